@@ -1,0 +1,399 @@
+// differt2d_b200 — the C ABI (include/differt2d_b200.h): argument checking, parameter packing,
+// candidate enumeration (host + integer CUDA kernel), host-buffer staging, FP32 peak probe.
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "d2d_launch.h"
+
+namespace {
+
+thread_local std::string g_err;
+std::atomic<long long> g_launches{0};
+
+int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+int cuda_fail(int e, const char* where) {
+    return fail(D2D_ERR_CUDA, std::string(where) + ": " + cudaGetErrorString((cudaError_t)e));
+}
+
+// allowed (visitable) objects in ascending order — scene.py:158-160 disconnects the filtered nodes
+int build_blocked(int n, const int32_t* filter, int n_filter, uint32_t* blocked /*[D2D_MAX_OBJECTS/32]*/) {
+    std::memset(blocked, 0, sizeof(uint32_t) * (D2D_MAX_OBJECTS / 32));
+    if (n_filter < 0 || (n_filter > 0 && !filter)) return -1;
+    for (int i = 0; i < n_filter; ++i) {
+        const int j = filter[i];
+        if (j < 0 || j >= n) continue;  // disconnecting a node that does not exist is a no-op
+        blocked[j >> 5] |= 1u << (j & 31);
+    }
+    int m = 0;
+    for (int j = 0; j < n; ++j)
+        if (!((blocked[j >> 5] >> (j & 31)) & 1u)) ++m;
+    return m;
+}
+
+long long count_for(int m, int order) {
+    if (order == 0) return 1;
+    if (m <= 0) return 0;
+    long long c = m;
+    for (int i = 1; i < order; ++i) {
+        c *= (m - 1);
+        if (c > (1LL << 62) / (m > 1 ? m : 2)) return -2;  // overflow guard
+    }
+    return c;
+}
+
+struct BlockedMask {
+    uint32_t w[D2D_MAX_OBJECTS / 32];
+};
+
+// Integer kernel: candidate index -> object-index sequence (lexicographic, no equal neighbours).
+// idx = sum_i digit_i * (m-1)^(k-1-i), digit_0 in [0,m), digit_i in [0,m-1);
+// position_i = digit_i + (digit_i >= position_{i-1}); object = allowed[position_i].
+__global__ void candidates_kernel(const BlockedMask mask, const int n, const int m, const int order,
+                                  const long long count, int32_t* __restrict__ out) {
+    __shared__ short allowed[D2D_MAX_OBJECTS];
+    if (threadIdx.x == 0) {
+        int q = 0;
+        for (int j = 0; j < n; ++j)
+            if (!((mask.w[j >> 5] >> (j & 31)) & 1u)) allowed[q++] = (short)j;
+    }
+    __syncthreads();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < count; idx += stride) {
+        long long rem = idx;
+        int digits[D2D_MAX_ORDER];
+        for (int i = order - 1; i >= 1; --i) {
+            digits[i] = (int)(rem % (m - 1));
+            rem /= (m - 1);
+        }
+        digits[0] = (int)rem;
+        int prev = -1;
+        for (int i = 0; i < order; ++i) {
+            int pos = digits[i];
+            if (i > 0 && pos >= prev) ++pos;
+            out[idx * order + i] = allowed[pos];
+            prev = pos;
+        }
+    }
+}
+
+// register-resident FMA chains: 16 independent accumulators per thread
+__global__ void __launch_bounds__(256) fma_peak_kernel(float* sink, int iters) {
+    float a[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = 1.0f + 1e-3f * (float)(threadIdx.x + i);
+    const float x = 0.999f + 1e-7f * (float)blockIdx.x, y = 1e-4f;
+    for (int it = 0; it < iters; ++it) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) a[i] = fmaf(a[i], x, y);
+        }
+    }
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) s += a[i];
+    if (s == 12345.678f) sink[0] = s;  // never true in practice; keeps the chains alive
+}
+
+int pack(const D2DProblem* p, d2d::KParams& k) {
+    if (!p) return fail(D2D_ERR_INVALID_ARGUMENT, "problem is NULL");
+    if (p->n_objects < 0 || p->n_objects > D2D_MAX_OBJECTS)
+        return fail(D2D_ERR_UNSUPPORTED, "n_objects outside [0, D2D_MAX_OBJECTS]");
+    if (p->n_objects > 0 && !p->objects_xys) return fail(D2D_ERR_INVALID_ARGUMENT, "objects_xys is NULL");
+    if (p->min_order < 0 || p->max_order < p->min_order)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "need 0 <= min_order <= max_order");
+    if (p->max_order > D2D_MAX_ORDER) return fail(D2D_ERR_UNSUPPORTED, "max_order > D2D_MAX_ORDER");
+    if (p->n_fixed < 0 || p->n_grid < 0) return fail(D2D_ERR_INVALID_ARGUMENT, "negative sizes");
+    if ((p->n_fixed > 0 && !p->fixed_xy) || (p->n_grid > 0 && !p->grid_xy))
+        return fail(D2D_ERR_INVALID_ARGUMENT, "fixed_xy / grid_xy is NULL");
+    if (p->grid_role != D2D_GRID_RECEIVERS && p->grid_role != D2D_GRID_TRANSMITTERS)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "bad grid_role");
+    if (p->mode < D2D_MODE_HARD || p->mode > D2D_MODE_SIGMOID) return fail(D2D_ERR_INVALID_ARGUMENT, "bad mode");
+    if (p->method < D2D_METHOD_IMAGE || p->method > D2D_METHOD_MINPATH)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "bad method");
+    if (p->fun != D2D_FUN_RECEIVED_POWER && p->fun != D2D_FUN_LENGTH_SQUARED)
+        return fail(D2D_ERR_UNSUPPORTED, "fun must be received_power or length_squared");
+    if (p->mode != D2D_MODE_HARD && !p->alpha_dev && !(p->alpha > 0.0f))
+        return fail(D2D_ERR_INVALID_ARGUMENT, "alpha must be > 0 (activations must be non-decreasing)");
+    if (p->method != D2D_METHOD_IMAGE && p->steps < 1)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "steps must be >= 1 (optimize.py:96 indexes losses[-1])");
+    if (p->grad_mode != D2D_GRAD_CLEAN) return fail(D2D_ERR_UNSUPPORTED, "only D2D_GRAD_CLEAN is implemented");
+    std::memset(&k, 0, sizeof(k));
+    k.xys = p->objects_xys;
+    k.kinds = p->object_kinds;
+    k.phis = p->object_phis;
+    k.fixed = p->fixed_xy;
+    k.grid = p->grid_xy;
+    k.x0 = p->x0;
+    k.alpha_dev = p->alpha_dev;
+    k.R = p->n_grid;
+    k.N = p->n_objects;
+    k.T = p->n_fixed;
+    k.min_order = p->min_order;
+    k.max_order = p->max_order;
+    k.steps = p->steps;
+    k.fun = p->fun;
+    k.reduce_all = p->reduce_all ? 1 : 0;
+    k.alpha = p->alpha;
+    k.tol = p->tol;
+    k.patch = p->patch;
+    k.lr = p->lr;
+    // utils.py:52-54 — Python folds r_coef**n and height*height in double, JAX then casts to f32
+    k.h2 = (float)((double)p->height * (double)p->height);
+    for (int i = 0; i <= d2d::kMaxOrder; ++i) k.rc_pow[i] = (float)std::pow((double)p->r_coef, (double)i);
+    const int m = build_blocked(p->n_objects, p->filter_nodes, p->n_filter, k.blocked);
+    if (m < 0) return fail(D2D_ERR_INVALID_ARGUMENT, "bad filter_nodes");
+    long long total = 0;
+    for (int o = p->min_order; o <= p->max_order; ++o) {
+        const long long c = count_for(m, o);
+        if (c < 0) return fail(D2D_ERR_UNSUPPORTED, "candidate count overflows int64");
+        total += c;
+    }
+    k.C_total = total;
+    return D2D_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+void d2d_problem_defaults(D2DProblem* p) {
+    if (!p) return;
+    std::memset(p, 0, sizeof(*p));
+    p->grid_role = D2D_GRID_RECEIVERS;
+    p->min_order = 0;
+    p->max_order = 1;  // scene.py:1817
+    p->method = D2D_METHOD_IMAGE;
+    p->steps = 100;  // optimize.py:49
+    p->lr = 0.1f;    // optimize.py:83
+    p->mode = D2D_MODE_HARD;
+    p->alpha = 100.0f;  // defaults.py:3
+    p->tol = 1e-2f;     // geometry.py:915
+    p->patch = 0.0f;    // defaults.py:7
+    p->fun = D2D_FUN_RECEIVED_POWER;
+    p->r_coef = 0.5f;  // defaults.py:12
+    p->height = 0.1f;  // defaults.py:15
+    p->grad_mode = D2D_GRAD_CLEAN;
+}
+
+int64_t d2d_candidates_count(int32_t n_objects, int32_t order, const int32_t* filter_nodes, int32_t n_filter) {
+    if (n_objects < 0 || n_objects > D2D_MAX_OBJECTS || order < 0) return -1;
+    uint32_t blocked[D2D_MAX_OBJECTS / 32];
+    const int m = build_blocked(n_objects, filter_nodes, n_filter, blocked);
+    if (m < 0) return -1;
+    return count_for(m, order);
+}
+
+int d2d_candidates_host(int32_t n_objects, int32_t order, const int32_t* filter_nodes, int32_t n_filter,
+                        int32_t* out) {
+    if (n_objects < 0 || n_objects > D2D_MAX_OBJECTS || order < 0 || order > D2D_MAX_ORDER)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "bad n_objects / order");
+    uint32_t blocked[D2D_MAX_OBJECTS / 32];
+    const int m = build_blocked(n_objects, filter_nodes, n_filter, blocked);
+    if (m < 0) return fail(D2D_ERR_INVALID_ARGUMENT, "bad filter_nodes");
+    if (order == 0 || !out) return D2D_OK;
+    if (m == 0 || (order > 1 && m < 2)) return D2D_OK;
+    std::vector<int> allowed;
+    for (int j = 0; j < n_objects; ++j)
+        if (!((blocked[j >> 5] >> (j & 31)) & 1u)) allowed.push_back(j);
+    // odometer over positions in `allowed`
+    int pos[D2D_MAX_ORDER];
+    for (int i = 0; i < order; ++i) pos[i] = i & 1;
+    long long row = 0;
+    for (;;) {
+        for (int i = 0; i < order; ++i) out[row * order + i] = allowed[pos[i]];
+        ++row;
+        int i = order - 1;
+        for (; i >= 0; --i) {
+            int v = pos[i] + 1;
+            if (i > 0 && v == pos[i - 1]) ++v;
+            if (v < m) {
+                pos[i] = v;
+                for (int j = i + 1; j < order; ++j) pos[j] = (pos[j - 1] == 0) ? 1 : 0;
+                break;
+            }
+        }
+        if (i < 0) break;
+    }
+    return D2D_OK;
+}
+
+int d2d_candidates_device(int32_t n_objects, int32_t order, const int32_t* filter_nodes, int32_t n_filter,
+                          int32_t* out, void* stream) {
+    if (n_objects < 0 || n_objects > D2D_MAX_OBJECTS || order < 0 || order > D2D_MAX_ORDER)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "bad n_objects / order");
+    BlockedMask mask;
+    const int m = build_blocked(n_objects, filter_nodes, n_filter, mask.w);
+    if (m < 0) return fail(D2D_ERR_INVALID_ARGUMENT, "bad filter_nodes");
+    const long long count = count_for(m, order);
+    if (count < 0) return fail(D2D_ERR_UNSUPPORTED, "candidate count overflows int64");
+    if (order == 0 || count == 0) return D2D_OK;
+    if (!out) return fail(D2D_ERR_INVALID_ARGUMENT, "out is NULL");
+    const int block = 256;
+    long long nblk = (count + block - 1) / block;
+    if (nblk > 148 * 16) nblk = 148 * 16;
+    candidates_kernel<<<(unsigned)nblk, block, 0, (cudaStream_t)stream>>>(mask, n_objects, m, order, count, out);
+    g_launches += 1;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? D2D_OK : cuda_fail(e, "candidates_kernel");
+}
+
+int64_t d2d_problem_num_candidates(const D2DProblem* p) {
+    d2d::KParams k;
+    if (pack(p, k) != D2D_OK) return -1;
+    return k.C_total;
+}
+
+int d2d_power_fwd(const D2DProblem* p, float* Z, float* valid_out, void* stream) {
+    d2d::KParams k;
+    const int rc = pack(p, k);
+    if (rc != D2D_OK) return rc;
+    if (!Z && p->n_grid > 0 && p->n_fixed > 0) return fail(D2D_ERR_INVALID_ARGUMENT, "Z is NULL");
+    if (p->method != D2D_METHOD_IMAGE && !p->x0 && p->max_order > 0)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "Fermat/MinPath need x0 (initial guesses per candidate)");
+    long long n = 0;
+    const int e = d2d::launch_power_fwd(k, p->mode, p->grid_role, p->method, Z, valid_out, (cudaStream_t)stream, &n);
+    g_launches += n;
+    return e == 0 ? D2D_OK : cuda_fail(e, "power_fwd_kernel");
+}
+
+int d2d_power_bwd(const D2DProblem* p, const float* Zbar, float* Z_out, float* grid_bar, float* objects_bar,
+                  float* phis_bar, float* fixed_bar, float* alpha_bar, void* stream) {
+    d2d::KParams k;
+    const int rc = pack(p, k);
+    if (rc != D2D_OK) return rc;
+    if (p->method != D2D_METHOD_IMAGE)
+        return fail(D2D_ERR_UNSUPPORTED, "reverse mode is implemented for ImagePath only (Fermat/MinPath: forward)");
+    d2d::BwdOut out{Z_out, grid_bar, objects_bar, phis_bar, fixed_bar, alpha_bar};
+    long long n = 0;
+    const int e = d2d::launch_power_bwd(k, p->mode, p->grid_role, p->method, Zbar, out, (cudaStream_t)stream, &n);
+    g_launches += n;
+    return e == 0 ? D2D_OK : cuda_fail(e, "power_bwd_kernel");
+}
+
+// ---- host-buffer entry ---------------------------------------------------------------------------
+namespace {
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int dev = -1;
+    int ensure(size_t n, int device) {
+        if (n <= cap && dev == device && p) return 0;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        const cudaError_t e = cudaMalloc(&p, n < 256 ? 256 : n);
+        if (e != cudaSuccess) return (int)e;
+        cap = n < 256 ? 256 : n;
+        dev = device;
+        return 0;
+    }
+};
+std::mutex g_host_mu;
+DevBuf g_in, g_out;
+cudaStream_t g_host_stream = nullptr;
+int g_host_stream_dev = -1;
+}  // namespace
+
+int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* grid_bar, float* objects_bar,
+                   float* phis_bar, float* fixed_bar, float* alpha_bar, int32_t device) {
+    if (!hp) return fail(D2D_ERR_INVALID_ARGUMENT, "problem is NULL");
+    std::lock_guard<std::mutex> lock(g_host_mu);
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
+    if (!g_host_stream || g_host_stream_dev != device) {
+        if ((e = cudaStreamCreateWithFlags(&g_host_stream, cudaStreamNonBlocking)) != cudaSuccess)
+            return cuda_fail(e, "cudaStreamCreate");
+        g_host_stream_dev = device;
+    }
+    cudaStream_t s = g_host_stream;
+    const size_t N = (size_t)hp->n_objects, T = (size_t)hp->n_fixed, R = (size_t)hp->n_grid;
+    const size_t Tout = hp->reduce_all ? 1 : T;
+    D2DProblem dp = *hp;
+    dp.alpha_dev = nullptr;
+    if (hp->alpha_dev) dp.alpha = *hp->alpha_dev;  // host scalar in this entry
+    const long long C = d2d_problem_num_candidates(&dp);
+    if (C < 0) return D2D_ERR_INVALID_ARGUMENT;
+    auto al = [](size_t n) { return (n + 255) / 256 * 256; };
+    // input arena
+    const size_t o_xys = 0, o_kind = o_xys + al(N * 16), o_phi = o_kind + al(N), o_fix = o_phi + al(N * 4),
+                 o_grid = o_fix + al(T * 8), o_x0 = o_grid + al(R * 8),
+                 o_zbar = o_x0 + al(hp->x0 ? (size_t)C * hp->max_order * 4 : 0),
+                 in_total = o_zbar + al(Zbar ? Tout * R * 4 : 0);
+    int rc = g_in.ensure(in_total, device);
+    if (rc) return cuda_fail(rc, "cudaMalloc(inputs)");
+    char* din = (char*)g_in.p;
+    auto h2d = [&](size_t off, const void* src, size_t n) {
+        if (src && n) cudaMemcpyAsync(din + off, src, n, cudaMemcpyHostToDevice, s);
+    };
+    h2d(o_xys, hp->objects_xys, N * 16);
+    h2d(o_kind, hp->object_kinds, N);
+    h2d(o_phi, hp->object_phis, N * 4);
+    h2d(o_fix, hp->fixed_xy, T * 8);
+    h2d(o_grid, hp->grid_xy, R * 8);
+    if (hp->x0) h2d(o_x0, hp->x0, (size_t)C * hp->max_order * 4);
+    if (Zbar) h2d(o_zbar, Zbar, Tout * R * 4);
+    dp.objects_xys = (const float*)(din + o_xys);
+    dp.object_kinds = hp->object_kinds ? (const uint8_t*)(din + o_kind) : nullptr;
+    dp.object_phis = hp->object_phis ? (const float*)(din + o_phi) : nullptr;
+    dp.fixed_xy = (const float*)(din + o_fix);
+    dp.grid_xy = (const float*)(din + o_grid);
+    dp.x0 = hp->x0 ? (const float*)(din + o_x0) : nullptr;
+    // output arena
+    const bool want_bwd = grid_bar || objects_bar || phis_bar || fixed_bar || alpha_bar;
+    const size_t q_z = 0, q_gb = q_z + al(Tout * R * 4), q_ob = q_gb + al(grid_bar ? Tout * R * 8 : 0),
+                 q_pb = q_ob + al(N * 16), q_fb = q_pb + al(N * 4), q_ab = q_fb + al(T * 8), out_total = q_ab + 256;
+    rc = g_out.ensure(out_total, device);
+    if (rc) return cuda_fail(rc, "cudaMalloc(outputs)");
+    char* dout = (char*)g_out.p;
+    if (want_bwd) {
+        rc = d2d_power_bwd(&dp, Zbar ? (const float*)(din + o_zbar) : nullptr, Z ? (float*)(dout + q_z) : nullptr,
+                           grid_bar ? (float*)(dout + q_gb) : nullptr, objects_bar ? (float*)(dout + q_ob) : nullptr,
+                           phis_bar ? (float*)(dout + q_pb) : nullptr, fixed_bar ? (float*)(dout + q_fb) : nullptr,
+                           alpha_bar ? (float*)(dout + q_ab) : nullptr, s);
+    } else {
+        rc = d2d_power_fwd(&dp, (float*)(dout + q_z), nullptr, s);
+    }
+    if (rc != D2D_OK) return rc;
+    auto d2h = [&](void* dst, size_t off, size_t n) {
+        if (dst && n) cudaMemcpyAsync(dst, dout + off, n, cudaMemcpyDeviceToHost, s);
+    };
+    d2h(Z, q_z, Tout * R * 4);
+    d2h(grid_bar, q_gb, Tout * R * 8);
+    d2h(objects_bar, q_ob, N * 16);
+    d2h(phis_bar, q_pb, N * 4);
+    d2h(fixed_bar, q_fb, T * 8);
+    d2h(alpha_bar, q_ab, 4);
+    e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) return cuda_fail(e, "d2d_power_host");
+    return D2D_OK;
+}
+
+int64_t d2d_launch_count(void) { return g_launches.load(); }
+
+int d2d_fma_peak_launch(float* sink, int32_t iters, double* flops, void* stream) {
+    if (!sink || iters <= 0) return fail(D2D_ERR_INVALID_ARGUMENT, "bad arguments");
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int blocks = sms * 8, threads = 256;
+    fma_peak_kernel<<<blocks, threads, 0, (cudaStream_t)stream>>>(sink, iters);
+    g_launches += 1;
+    if (flops) *flops = (double)blocks * threads * (double)iters * 4.0 * 16.0 * 2.0;
+    const cudaError_t e = cudaGetLastError();
+    return e == cudaSuccess ? D2D_OK : cuda_fail(e, "fma_peak_kernel");
+}
+
+const char* d2d_last_error(void) { return g_err.c_str(); }
+int32_t d2d_abi_version(void) { return D2D_ABI_VERSION; }
+
+}  // extern "C"

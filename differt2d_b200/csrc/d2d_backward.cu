@@ -1,0 +1,465 @@
+// differt2d_b200 — reverse-mode (VJP) kernel, by recomputation.
+//
+// Same mapping as the forward kernel (one thread per grid point, candidates walked in list order
+// by the whole CTA).  Nothing is stored by the forward pass: each path is re-traced, and only paths
+// whose validity is non-zero run the reverse sweep.  In smooth mode the validity is
+// min(act(onx), 1 - act(interx), act(lx)) and every fold is a min/max, so the cotangent follows a
+// single chain: the arg-min comparison of on_objects, OR the arg-max (segment, object) occlusion
+// test, OR the loss — the reverse sweep of the occlusion double loop costs one test, not (k+1)N.
+//
+// Per-grid-point cotangents are written directly (disjoint).  Scene-parameter cotangents are
+// reduced warp (shuffle) -> CTA (shared-memory atomics) -> device (global fp32 atomics); the
+// multi-GPU all-reduce of these few KB happens in the host layer (differt2d_b200/distributed.py).
+#include "d2d_launch.h"
+#include "d2d_solver.cuh"
+
+namespace d2d {
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Reverse sweep of one ImagePath.  Returns valid * fun; when the path carries gradient, `has` is set
+// and tx_bar / rx_bar / alpha_bar / oa[] / occ_* are filled (not accumulated).
+template <int MODE, int K>
+__device__ __forceinline__ float path_vjp_image(const SceneTab& T, const KParams& p, const float alpha,
+                                                const Cand<K>& cd, const float2 tx, const float2 rx,
+                                                const float zbar, bool& has, float2& tx_bar, float2& rx_bar,
+                                                float& alpha_bar, ObjAdj (&oa)[K > 0 ? K : 1], int& occ_j,
+                                                float4& occ_bar) {
+    has = false;
+    occ_j = -1;
+    // ---- recompute the forward, keeping what the reverse sweep needs --------------------------
+    float2 X[K + 2];
+    float2 I[K + 1];
+    X[0] = tx;
+    X[K + 1] = rx;
+    I[0] = tx;
+#pragma unroll
+    for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[cd.c[i]], T.w1[cd.c[i]]);
+    {
+        float2 q = rx;
+#pragma unroll
+        for (int i = K - 1; i >= 0; --i) {
+            q = back_project(q, I[i + 1], T.w0[cd.c[i]], T.w1[cd.c[i]]);
+            X[i + 1] = q;
+        }
+    }
+    float onx = CUDART_INF_F;
+    int on_i = -1;
+    float on_s = 0.f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const int j = cd.c[i];
+        if (T.kind[j] == D2D_KIND_VERTEX) continue;
+        const float s = to_parametric(X[i + 1], T.w0[j], T.w1[j]);
+        float x = fminf(s, 1.0f - s);
+        if (s != s) x = -CUDART_INF_F;
+        if (x < onx) { onx = x; on_i = i; on_s = s; }
+    }
+    float a_on = 1.0f;
+    if (MODE == D2D_MODE_HARD) {
+        if (!(onx >= 0.0f)) return 0.0f;
+    } else if (onx != CUDART_INF_F) {
+        a_on = act<MODE>(onx, alpha);
+        if (a_on == 0.0f) return 0.0f;
+    }
+    const float loss = path_loss<K>(T, cd, X);
+    const float lx = p.tol - loss;
+    float a_l = 1.0f;
+    if (MODE == D2D_MODE_HARD) {
+        if (!(lx > 0.0f)) return 0.0f;
+    } else {
+        if (lx != lx) return 0.0f;
+        a_l = act<MODE>(lx, alpha);
+        if (a_l == 0.0f) return 0.0f;
+    }
+    bool alive = true;
+    int seg = -1, jj = -1;
+    const float interx = intersects_x<MODE, K, true>(T, p.N, cd, X, alpha, alive, seg, jj);
+    if (!alive) return 0.0f;
+    float valid = 1.0f, a_in = 0.0f;
+    if (MODE != D2D_MODE_HARD) {
+        a_in = (interx == -CUDART_INF_F) ? 0.0f : act<MODE>(interx, alpha);
+        valid = fminf(fminf(a_on, 1.0f - a_in), a_l);
+        if (valid == 0.0f) return 0.0f;
+    }
+    float r;
+    const float val = path_value<K>(p, X, r);
+    const float contrib = valid * val;
+    if (zbar == 0.0f) return contrib;
+    has = true;
+
+    // ---- reverse sweep ----------------------------------------------------------------------------
+    float2 Xb[K + 2];
+#pragma unroll
+    for (int i = 0; i < K + 2; ++i) Xb[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < K; ++i) oa[i].zero();
+    alpha_bar = 0.f;
+
+    // (1) fun(path) : utils.py:52-54 / length**2 ; path_length geometry.py:199-203
+    {
+        const float val_bar = zbar * valid;
+        float r_bar;
+        if (p.fun == D2D_FUN_RECEIVED_POWER) r_bar = -val_bar * val * 2.0f * r / (p.h2 + r * r);
+        else r_bar = val_bar * 2.0f * r;
+#pragma unroll
+        for (int i = 0; i <= K; ++i) {
+            const float dx = (X[i + 1].x - X[i].x) + kEps32;
+            const float dy = (X[i + 1].y - X[i].y) + kEps32;
+            const float len = sqrtf(dx * dx + dy * dy);
+            if (len > 0.0f) {
+                const float c = r_bar / len;
+                Xb[i + 1].x += c * dx; Xb[i + 1].y += c * dy;
+                Xb[i].x -= c * dx; Xb[i].y -= c * dy;
+            }
+        }
+    }
+
+    // (2) validity (smooth logic only) : geometry.py:947-963, logic.py:511-512
+    if (MODE != D2D_MODE_HARD) {
+        const float v1 = a_on, v2 = 1.0f - a_in, v3 = a_l;
+        const int cnt = (v1 == valid) + (v2 == valid) + (v3 == valid);
+        const float share = zbar * val / (float)cnt;  // jnp.min splits evenly among ties
+        if (v1 == valid && on_i >= 0) {
+            const float dz = act_dz<MODE>(onx, alpha);
+            const float onx_bar = share * alpha * dz;
+            alpha_bar += share * onx * dz;
+            const float one_minus = 1.0f - on_s;
+            float s_bar = 0.f;
+            if (on_s < one_minus) s_bar = onx_bar;
+            else if (on_s > one_minus) s_bar = -onx_bar;
+            if (s_bar != 0.f) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    if (i != on_i) continue;
+                    const float4 w0 = T.w0[cd.c[i]];
+                    const float4 w1 = T.w1[cd.c[i]];
+                    const float wx = X[i + 1].x - w0.x, wy = X[i + 1].y - w0.y;
+                    const float k = s_bar / w1.z;
+                    Xb[i + 1].x += k * w0.z; Xb[i + 1].y += k * w0.w;
+                    oa[i].p1.x -= k * w0.z; oa[i].p1.y -= k * w0.w;
+                    oa[i].t.x += k * wx; oa[i].t.y += k * wy;
+                    oa[i].tt += -k * on_s;
+                }
+            }
+        }
+        if (v3 == valid) {
+            const float dz = act_dz<MODE>(lx, alpha);
+            const float loss_bar = -share * alpha * dz;
+            alpha_bar += share * lx * dz;
+            if (loss_bar != 0.f) {
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    const int j = cd.c[i];
+                    residual_adj(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j], loss_bar, Xb[i], Xb[i + 1],
+                                 Xb[i + 2], oa[i].n, oa[i].phi);
+                }
+            }
+        }
+        if (v2 == valid && jj >= 0 && interx != -CUDART_INF_F) {
+            const float dz = act_dz<MODE>(interx, alpha);
+            const float ix_bar = -share * alpha * dz;
+            alpha_bar += -share * interx * dz;
+            if (ix_bar != 0.f) {
+                float2 P = X[0], Q = X[1];
+#pragma unroll
+                for (int i = 0; i <= K; ++i)
+                    if (i == seg) { P = X[i]; Q = X[i + 1]; }
+                const float4 w = T.w2[jj];
+                const float2 B = make_float2(P.x - Q.x, P.y - Q.y);
+                const float Cx = w.x - P.x, Cy = w.y - P.y;
+                const float a = B.y * Cx - B.x * Cy;
+                const float b = w.z * Cy - w.w * Cx;
+                const float d = w.w * B.x - w.z * B.y;
+                const float ta = a / d, tb = b / d;
+                const float x1 = ta + kTolSeg, x2 = kHiSeg - ta, x3 = tb + kTolSeg, x4 = kHiSeg - tb;
+                const float hx = fminf(fminf(x1, x2), fminf(x3, x4));
+                const int ties = (x1 == hx) + (x2 == hx) + (x3 == hx) + (x4 == hx);
+                const float g = ix_bar / (float)ties;
+                const float ta_bar = (x1 == hx ? g : 0.f) - (x2 == hx ? g : 0.f);
+                const float tb_bar = (x3 == hx ? g : 0.f) - (x4 == hx ? g : 0.f);
+                const float a_bar = ta_bar / d, b_bar = tb_bar / d;
+                const float d_bar = -(ta_bar * ta + tb_bar * tb) / d;
+                float2 Bb, Cb, Ab;
+                Bb.y = a_bar * Cx - d_bar * w.z;
+                Bb.x = -a_bar * Cy + d_bar * w.w;
+                Cb.x = a_bar * B.y - b_bar * w.w;
+                Cb.y = -a_bar * B.x + b_bar * w.z;
+                Ab.x = b_bar * Cy - d_bar * B.y;
+                Ab.y = -b_bar * Cx + d_bar * B.x;
+                const float2 Pb = make_float2(Bb.x - Cb.x, Bb.y - Cb.y);
+#pragma unroll
+                for (int i = 0; i <= K; ++i)
+                    if (i == seg) {
+                        Xb[i].x += Pb.x; Xb[i].y += Pb.y;
+                        Xb[i + 1].x -= Bb.x; Xb[i + 1].y -= Bb.y;
+                    }
+                // P1' = (1+patch) P1 - patch P2 ; P2' = (1+patch) P2 - patch P1 ; A = P2' - P1' ; C = P1' - P
+                const float2 p1p = make_float2(Cb.x - Ab.x, Cb.y - Ab.y);
+                const float2 p2p = Ab;
+                const float q = p.patch;
+                occ_j = jj;
+                occ_bar = make_float4((1.0f + q) * p1p.x - q * p2p.x, (1.0f + q) * p1p.y - q * p2p.y,
+                                      (1.0f + q) * p2p.x - q * p1p.x, (1.0f + q) * p2p.y - q * p1p.y);
+            }
+        }
+    }
+
+    // (3) backward scan of the image method : geometry.py:1093-1107 (clean `where`)
+    float2 Ib[K + 1];
+#pragma unroll
+    for (int i = 0; i <= K; ++i) Ib[i] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const float4 w0 = T.w0[cd.c[i]];
+        const float4 w1 = T.w1[cd.c[i]];
+        const float2 qb = Xb[i + 1];
+        const float2 pt = X[i + 2];
+        const float ux = pt.x - I[i + 1].x, uy = pt.y - I[i + 1].y;
+        const float vx = w0.x - pt.x, vy = w0.y - pt.y;
+        const float un = ux * w1.x + uy * w1.y;
+        const float vn = vx * w1.x + vy * w1.y;
+        Xb[i + 2].x += qb.x; Xb[i + 2].y += qb.y;
+        if (un != 0.0f) {
+            const float g = vn / un;
+            float ubx = g * qb.x, uby = g * qb.y;
+            const float gb = qb.x * ux + qb.y * uy;
+            const float vnb = gb / un;
+            const float unb = -gb * g / un;
+            ubx += unb * w1.x; uby += unb * w1.y;
+            oa[i].n.x += unb * ux + vnb * vx;
+            oa[i].n.y += unb * uy + vnb * vy;
+            const float vbx = vnb * w1.x, vby = vnb * w1.y;
+            Xb[i + 2].x += ubx - vbx; Xb[i + 2].y += uby - vby;
+            Ib[i + 1].x -= ubx; Ib[i + 1].y -= uby;
+            oa[i].p1.x += vbx; oa[i].p1.y += vby;
+        }
+    }
+    // (4) forward scan (mirror chain) : geometry.py:1086-1091, 652-670
+#pragma unroll
+    for (int i = K - 1; i >= 0; --i) {
+        const float4 w0 = T.w0[cd.c[i]];
+        const float4 w1 = T.w1[cd.c[i]];
+        const float wx = I[i].x - w0.x, wy = I[i].y - w0.y;
+        const float cc = 2.0f * (wx * w1.x + wy * w1.y);
+        const float2 ib = Ib[i + 1];
+        const float ccb = -(ib.x * w1.x + ib.y * w1.y);
+        const float dotb = 2.0f * ccb;
+        oa[i].n.x += -cc * ib.x + dotb * wx;
+        oa[i].n.y += -cc * ib.y + dotb * wy;
+        const float wbx = dotb * w1.x, wby = dotb * w1.y;
+        Ib[i].x += ib.x + wbx; Ib[i].y += ib.y + wby;
+        oa[i].p1.x -= wbx; oa[i].p1.y -= wby;
+    }
+    tx_bar = make_float2(Xb[0].x + Ib[0].x, Xb[0].y + Ib[0].y);
+    rx_bar = Xb[K + 1];
+    return contrib;
+}
+
+struct BwdAcc {
+    float2 grid_bar;   // this thread's grid point, current fixed point
+    float2 fixed_bar;  // current fixed point (to be reduced over the grid)
+    float alpha_bar;
+    float acc;
+};
+
+template <int MODE, int K, bool TXGRID>
+__device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& p, const float alpha,
+                                              const float2 tx, const float2 rx, const bool active, const float zbar,
+                                              BwdAcc& A, float* s_obj, float* s_phi) {
+    Odometer<K> od;
+    if (!od.first(T.n_allowed)) return;
+    constexpr int KK = K > 0 ? K : 1;
+    do {
+        Cand<K> cd;
+#pragma unroll
+        for (int i = 0; i < K; ++i) cd.c[i] = T.allowed[od.pos[i]];
+        bool has = false;
+        float2 txb = make_float2(0.f, 0.f), rxb = make_float2(0.f, 0.f);
+        float ab = 0.f;
+        ObjAdj oa[KK];
+        int occ_j = -1;
+        float4 occ_bar = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (active) {
+            const float c = path_vjp_image<MODE, K>(T, p, alpha, cd, tx, rx, zbar, has, txb, rxb, ab, oa, occ_j, occ_bar);
+            A.acc = A.acc + c;
+        }
+        if (has) {
+            const float2 gb = TXGRID ? txb : rxb;
+            const float2 fb = TXGRID ? rxb : txb;
+            A.grid_bar.x += gb.x; A.grid_bar.y += gb.y;
+            A.fixed_bar.x += fb.x; A.fixed_bar.y += fb.y;
+            A.alpha_bar += ab;
+            if (occ_j >= 0 && s_obj) {
+                atomicAdd(&s_obj[4 * occ_j + 0], occ_bar.x);
+                atomicAdd(&s_obj[4 * occ_j + 1], occ_bar.y);
+                atomicAdd(&s_obj[4 * occ_j + 2], occ_bar.z);
+                atomicAdd(&s_obj[4 * occ_j + 3], occ_bar.w);
+            }
+        }
+        if (K > 0 && s_obj && __any_sync(0xffffffffu, has)) {
+            // every lane holds the same candidate: reduce the interacting objects' cotangents in the warp
+#pragma unroll
+            for (int i = 0; i < K; ++i) {
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                float ph = 0.f;
+                if (has) {
+                    v = oa[i].to_vertices(T.w0[cd.c[i]], T.w1[cd.c[i]]);
+                    ph = oa[i].phi;
+                }
+                v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+                const bool ris = T.kind[cd.c[i]] == D2D_KIND_RIS;
+                if (ris) ph = warp_sum(ph);
+                if ((threadIdx.x & 31) == 0) {
+                    atomicAdd(&s_obj[4 * cd.c[i] + 0], v.x);
+                    atomicAdd(&s_obj[4 * cd.c[i] + 1], v.y);
+                    atomicAdd(&s_obj[4 * cd.c[i] + 2], v.z);
+                    atomicAdd(&s_obj[4 * cd.c[i] + 3], v.w);
+                    if (ris) atomicAdd(&s_phi[cd.c[i]], ph);
+                }
+            }
+        }
+    } while (od.next(T.n_allowed));
+}
+
+template <int MODE, bool TXGRID>
+__global__ void __launch_bounds__(128) power_bwd_kernel(const KParams p, const float* __restrict__ Zbar,
+                                                        const BwdOut out) {
+    extern __shared__ __align__(16) unsigned char smem[];
+    __shared__ int s_count;
+    __shared__ float s_red[4][4];
+    SceneTab T = carve_tab(smem, p.N);
+    const bool want_obj = out.objects_bar != nullptr || out.phis_bar != nullptr;
+    float* s_obj = nullptr;
+    float* s_phi = nullptr;
+    if (want_obj) {
+        s_obj = reinterpret_cast<float*>(smem + ((scene_tab_bytes(p.N) + 15) / 16) * 16);
+        s_phi = s_obj + 4 * p.N;
+        for (int j = threadIdx.x; j < 5 * p.N; j += blockDim.x) s_obj[j] = 0.f;
+    }
+    build_tab(T, p, &s_count);
+    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = r < p.R;
+    const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
+    const float2 g = active ? reinterpret_cast<const float2*>(p.grid)[r] : make_float2(0.f, 0.f);
+    float zsum = 0.0f;
+    float2 gsum = make_float2(0.f, 0.f);
+    float alpha_total = 0.f;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int t = 0; t < p.T; ++t) {
+        const float2 fx = reinterpret_cast<const float2*>(p.fixed)[t];
+        const float2 tx = TXGRID ? g : fx;
+        const float2 rx = TXGRID ? fx : g;
+        float zbar = 0.f;
+        if (active) zbar = Zbar ? Zbar[p.reduce_all ? r : (long long)t * p.R + r] : 1.0f;
+        BwdAcc A;
+        A.grid_bar = A.fixed_bar = make_float2(0.f, 0.f);
+        A.alpha_bar = 0.f;
+        A.acc = 0.f;
+        for (int k = p.min_order; k <= p.max_order; ++k) {
+            switch (k) {
+                case 0: run_order_bwd<MODE, 0, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
+                case 1: run_order_bwd<MODE, 1, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
+                case 2: run_order_bwd<MODE, 2, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
+                case 3: run_order_bwd<MODE, 3, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
+                case 4: run_order_bwd<MODE, 4, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
+                default: break;
+            }
+        }
+        if (active) {
+            if (p.reduce_all) {
+                zsum = zsum + A.acc;
+                gsum.x += A.grid_bar.x; gsum.y += A.grid_bar.y;
+            } else {
+                if (out.Z) out.Z[(long long)t * p.R + r] = A.acc;
+                if (out.grid_bar) reinterpret_cast<float2*>(out.grid_bar)[(long long)t * p.R + r] = A.grid_bar;
+            }
+        }
+        alpha_total += A.alpha_bar;
+        if (out.fixed_bar) {  // CTA reduction of this fixed point's cotangent
+            const float fxs = warp_sum(A.fixed_bar.x), fys = warp_sum(A.fixed_bar.y);
+            __syncthreads();
+            if (lane == 0) { s_red[warp][0] = fxs; s_red[warp][1] = fys; }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                float sx = 0.f, sy = 0.f;
+                for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { sx += s_red[w][0]; sy += s_red[w][1]; }
+                if (sx != 0.f) atomicAdd(&out.fixed_bar[2 * t + 0], sx);
+                if (sy != 0.f) atomicAdd(&out.fixed_bar[2 * t + 1], sy);
+            }
+        }
+    }
+    if (active && p.reduce_all) {
+        if (out.Z) out.Z[r] = zsum;
+        if (out.grid_bar) reinterpret_cast<float2*>(out.grid_bar)[r] = gsum;
+    }
+    if (out.alpha_bar) {
+        const float as = warp_sum(alpha_total);
+        __syncthreads();
+        if (lane == 0) s_red[warp][2] = as;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.f;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) s += s_red[w][2];
+            if (s != 0.f) atomicAdd(out.alpha_bar, s);
+        }
+    }
+    if (want_obj) {
+        __syncthreads();
+        for (int j = threadIdx.x; j < 4 * p.N; j += blockDim.x)
+            if (out.objects_bar && s_obj[j] != 0.f) atomicAdd(&out.objects_bar[j], s_obj[j]);
+        for (int j = threadIdx.x; j < p.N; j += blockDim.x)
+            if (out.phis_bar && s_phi[j] != 0.f) atomicAdd(&out.phis_bar[j], s_phi[j]);
+    }
+}
+
+template <int MODE, bool TXGRID>
+static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out, cudaStream_t stream) {
+    const int block = 128;
+    const long long nblk = (p.R + block - 1) / block;
+    size_t smem = ((scene_tab_bytes(p.N) + 15) / 16) * 16;
+    if (out.objects_bar || out.phis_bar) smem += (size_t)5 * p.N * sizeof(float);
+    auto kern = power_bwd_kernel<MODE, TXGRID>;
+    if (smem > 48 * 1024) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return (int)e;
+    }
+    kern<<<(unsigned)nblk, block, smem, stream>>>(p, Zbar, out);
+    return (int)cudaGetLastError();
+}
+
+int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, const float* Zbar, const BwdOut& out,
+                     cudaStream_t stream, long long* launches) {
+    if (method != D2D_METHOD_IMAGE) return (int)cudaErrorNotSupported;
+    cudaError_t e;
+    if (out.objects_bar && (e = cudaMemsetAsync(out.objects_bar, 0, sizeof(float) * 4 * p.N, stream)) != cudaSuccess) return (int)e;
+    if (out.phis_bar && (e = cudaMemsetAsync(out.phis_bar, 0, sizeof(float) * p.N, stream)) != cudaSuccess) return (int)e;
+    if (out.fixed_bar && (e = cudaMemsetAsync(out.fixed_bar, 0, sizeof(float) * 2 * p.T, stream)) != cudaSuccess) return (int)e;
+    if (out.alpha_bar && (e = cudaMemsetAsync(out.alpha_bar, 0, sizeof(float), stream)) != cudaSuccess) return (int)e;
+    if (p.R <= 0) return 0;
+    const bool txg = grid_role == D2D_GRID_TRANSMITTERS;
+    int rc;
+    switch (mode) {
+        case D2D_MODE_HARD:
+            rc = txg ? launch_bwd_one<D2D_MODE_HARD, true>(p, Zbar, out, stream)
+                     : launch_bwd_one<D2D_MODE_HARD, false>(p, Zbar, out, stream);
+            break;
+        case D2D_MODE_HARD_SIGMOID:
+            rc = txg ? launch_bwd_one<D2D_MODE_HARD_SIGMOID, true>(p, Zbar, out, stream)
+                     : launch_bwd_one<D2D_MODE_HARD_SIGMOID, false>(p, Zbar, out, stream);
+            break;
+        case D2D_MODE_SIGMOID:
+            rc = txg ? launch_bwd_one<D2D_MODE_SIGMOID, true>(p, Zbar, out, stream)
+                     : launch_bwd_one<D2D_MODE_SIGMOID, false>(p, Zbar, out, stream);
+            break;
+        default: return (int)cudaErrorInvalidValue;
+    }
+    if (launches) *launches += 1;
+    return rc;
+}
+
+}  // namespace d2d

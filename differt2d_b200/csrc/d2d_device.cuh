@@ -1,0 +1,277 @@
+// differt2d_b200 — device-side building blocks of the path-tracing kernels (sm_100a, FP32 CUDA cores).
+//
+// Arithmetic discipline.  The translation units that include this header are compiled with
+// `-fmad=false -prec-div=true -prec-sqrt=true -ftz=false`: every `*`, `+`, `-`, `/`, `sqrtf`
+// below is one IEEE-754 binary32 operation in the order written, which is the order of the
+// reference's Python (cited per function).  That makes the geometric quantities that feed the
+// hard-logic predicates bit-reproducible.  Where an approximate value is enough (the occlusion
+// pre-filter) fused multiply-adds are requested explicitly with fmaf() and the result is only
+// used to decide whether the exact expression has to be evaluated at all.
+//
+// Validity in "pre-activation" form.  The reference evaluates an activation per comparison and
+// folds them with min/max (logic.py:315-358).  Every activation is the same non-decreasing map
+// act(x) = f(alpha*x) (alpha > 0) applied to a difference x, and rounding-to-nearest keeps
+// monotone maps monotone, so   min_i act(x_i) == act(min_i x_i)   and   max_i act(x_i) ==
+// act(max_i x_i)   hold bit-for-bit.  The kernels therefore fold the *differences*
+//     onx     = min_i min(s_i - 0, 1 - s_i)                                   (geometry.py:841-854, 600-621)
+//     interx  = max_{seg,obj} min(ta + tol, (1+tol) - ta, tb + tol, (1+tol) - tb)   (geometry.py:153-173, 887-904)
+//     lx      = tol_loss - loss                                               (geometry.py:960)
+// and apply the activation three times per path instead of 2k + 4(k+1)N + 1 times.  In hard mode
+// the comparisons `x >= y` / `x <= y` / `x < y` are equivalent to sign tests of the rounded
+// differences (fl(a-b) has the sign of a-b), so the same folds serve both logics.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math_constants.h>
+#include <stdint.h>
+
+#include "../../include/differt2d_b200.h"
+
+namespace d2d {
+
+constexpr float kEps32 = 1.1920928955078125e-07f;  // geometry.py:200
+constexpr float kTolSeg = 0.005f;                  // geometry.py:89
+constexpr float kHiSeg = 1.0f + 0.005f;            // geometry.py:169  fl(1.0 + tol)
+constexpr float kHalfSpan = 0.505f;                // (hi - lo)/2 : hx ~= kHalfSpan - max(|ta-.5|,|tb-.5|)
+constexpr int kMaxOrder = D2D_MAX_ORDER;
+
+// ---- kernel parameters (by value) -----------------------------------------------------------
+struct KParams {
+    const float* xys;      // [N,2,2]
+    const uint8_t* kinds;  // [N] or nullptr
+    const float* phis;     // [N] or nullptr
+    const float* fixed;    // [T,2]
+    const float* grid;     // [R,2]
+    const float* x0;       // [C,max_order] or nullptr
+    const float* alpha_dev;
+    long long R;
+    int N, T;
+    int min_order, max_order;
+    int steps;
+    int fun, reduce_all;
+    long long C_total;     // candidates over all orders (columns of valid_out)
+    float alpha, tol, patch, lr;
+    float h2;                      // (float)(height*height), folded in double like Python does
+    float rc_pow[kMaxOrder + 1];   // (float)(r_coef**k)
+    uint32_t blocked[D2D_MAX_OBJECTS / 32];  // bit j set: object j is never visited (filter_objects)
+};
+
+// ---- shared-memory scene table ---------------------------------------------------------------
+// One entry per object, derived once per CTA from the raw vertices with the reference's formulas.
+struct SceneTab {
+    float4* w0;    // P1.x, P1.y, t.x, t.y                       Ray.origin/t   geometry.py:458-487
+    float4* w1;    // n.x, n.y, tt (0 -> 1), len(n_raw) (0 -> 1) Wall.normal :561-573, :596-597
+    float4* w2;    // P1'.x, P1'.y, A.x, A.y  (patched wall; A = 0 for a Vertex)   :632-635
+    float2* sc;    // sin(phi), cos(phi)                         RIS :707-708
+    int* kind;     // D2D_KIND_*
+    short* allowed;  // ascending list of visitable objects
+    int n_allowed;
+};
+
+__host__ __device__ inline size_t scene_tab_bytes(int N) {
+    return (size_t)N * (3 * sizeof(float4) + sizeof(float2) + sizeof(int) + sizeof(short)) + 64;
+}
+
+__device__ __forceinline__ SceneTab carve_tab(unsigned char* smem, int N) {
+    SceneTab T;
+    T.w0 = reinterpret_cast<float4*>(smem);
+    T.w1 = T.w0 + N;
+    T.w2 = T.w1 + N;
+    T.sc = reinterpret_cast<float2*>(T.w2 + N);
+    T.kind = reinterpret_cast<int*>(T.sc + N);
+    T.allowed = reinterpret_cast<short*>(T.kind + N);
+    T.n_allowed = 0;
+    return T;
+}
+
+// Builds the table cooperatively; must be called by every thread of the CTA.
+__device__ inline void build_tab(SceneTab& T, const KParams& p, int* s_count) {
+    const int N = p.N;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+        const float4 raw = reinterpret_cast<const float4*>(p.xys)[j];  // P1.x P1.y P2.x P2.y
+        const int kind = p.kinds ? (int)p.kinds[j] : D2D_KIND_WALL;
+        const float tx = raw.z - raw.x, ty = raw.w - raw.y;
+        // Wall.normal: n = normalize((t.y, -t.x))  geometry.py:568-572, 227-230
+        const float mx = ty, my = -tx;
+        float len = sqrtf(mx * mx + my * my);
+        if (len == 0.0f) len = 1.0f;
+        float tt = tx * tx + ty * ty;  // geometry.py:596-597
+        if (tt == 0.0f) tt = 1.0f;
+        T.w0[j] = make_float4(raw.x, raw.y, tx, ty);
+        T.w1[j] = make_float4(mx / len, my / len, tt, len);
+        // intersects_cartesian: origin - patch*t, dest + patch*t  geometry.py:632-635
+        const float p1x = raw.x - p.patch * tx, p1y = raw.y - p.patch * ty;
+        const float p2x = raw.z + p.patch * tx, p2y = raw.w + p.patch * ty;
+        float ax = p2x - p1x, ay = p2y - p1y;
+        if (kind == D2D_KIND_VERTEX) { ax = 0.0f; ay = 0.0f; }  // never occludes (geometry.py:405-414)
+        T.w2[j] = make_float4(p1x, p1y, ax, ay);
+        const float phi = p.phis ? p.phis[j] : 0.0f;
+        T.sc[j] = make_float2(sinf(phi), cosf(phi));
+        T.kind[j] = kind;
+    }
+    if (threadIdx.x == 0) {
+        int m = 0;
+        for (int j = 0; j < N; ++j)
+            if (!((p.blocked[j >> 5] >> (j & 31)) & 1u)) T.allowed[m++] = (short)j;
+        *s_count = m;
+    }
+    __syncthreads();
+    T.n_allowed = *s_count;
+}
+
+// ---- logic ----------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ float act(float x, float alpha) {
+    const float z = alpha * x;
+    if (MODE == D2D_MODE_SIGMOID) {
+        return 1.0f / (1.0f + expf(-z));  // logic.py:235
+    }
+    float v = z + 3.0f;  // logic.py:255  relu6(z + 3) / 6
+    v = fmaxf(v, 0.0f);
+    v = fminf(v, 6.0f);
+    return v / 6.0f;
+}
+
+// d/dz of f at z = alpha*x (the VJP rules of jnp.minimum/maximum give 1/2 at the kinks)
+template <int MODE>
+__device__ __forceinline__ float act_dz(float x, float alpha) {
+    const float z = alpha * x;
+    if (MODE == D2D_MODE_SIGMOID) {
+        const float s = 1.0f / (1.0f + expf(-z));
+        return s * (1.0f - s);
+    }
+    const float v = z + 3.0f;
+    float g = (v > 0.0f && v < 6.0f) ? 1.0f : 0.0f;
+    if (v == 0.0f || v == 6.0f) g = 0.5f;
+    return g / 6.0f;
+}
+
+// Threshold on the occlusion pre-filter measure m: any test with m >= cthr(interx) cannot raise
+// interx (hx ~= kHalfSpan - m up to a few ulp; the margin is generous on purpose).
+__device__ __forceinline__ float filter_threshold(float interx) {
+    const float c = kHalfSpan - interx;
+    return fmaf(fabsf(c), 4e-6f, c + 4e-6f);
+}
+
+// Smallest pre-activation that still matters: act(x) == 0 exactly for every x <= x_zero.
+template <int MODE>
+__device__ __forceinline__ float x_zero(float alpha) {
+    if (MODE == D2D_MODE_HARD) return 0.0f;  // only hx >= 0 matters (with margin from filter_threshold)
+    if (MODE == D2D_MODE_HARD_SIGMOID) return -3.0f / alpha - fabsf(4.0f / alpha) * 1e-5f;
+    return -CUDART_INF_F;  // sigmoid never reaches 0 in a useful range: every test may matter
+}
+
+// ---- geometry -------------------------------------------------------------------------------
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// Wall.image_of — geometry.py:652-670
+__device__ __forceinline__ float2 mirror(const float2 p, const float4 w0, const float4 w1) {
+    const float ix = p.x - w0.x, iy = p.y - w0.y;
+    const float cc = 2.0f * (ix * w1.x + iy * w1.y);
+    return make_float2(p.x - cc * w1.x, p.y - cc * w1.y);
+}
+
+// one step of the backward scan of ImagePath — geometry.py:1093-1107
+__device__ __forceinline__ float2 back_project(const float2 point, const float2 image, const float4 w0,
+                                               const float4 w1) {
+    const float ux = point.x - image.x, uy = point.y - image.y;
+    const float vx = w0.x - point.x, vy = w0.y - point.y;
+    const float un = ux * w1.x + uy * w1.y;
+    const float vn = vx * w1.x + vy * w1.y;
+    float2 q = point;
+    if (un != 0.0f) {
+        q.x = point.x + (vn * ux) / un;
+        q.y = point.y + (vn * uy) / un;
+    }
+    return q;
+}
+
+// normalize — geometry.py:206-230
+__device__ __forceinline__ float2 normalize2(const float2 v, float& len) {
+    len = sqrtf(v.x * v.x + v.y * v.y);
+    if (len == 0.0f) len = 1.0f;
+    return make_float2(v.x / len, v.y / len);
+}
+
+// Interactable.evaluate_cartesian — Wall geometry.py:641-650, RIS :698-711, Vertex :416-419
+__device__ __forceinline__ float residual(const int kind, const float2 a, const float2 b, const float2 c,
+                                          const float4 w1, const float2 sc) {
+    if (kind == D2D_KIND_VERTEX) return 0.0f;
+    float l;
+    const float2 r = normalize2(make_float2(c.x - b.x, c.y - b.y), l);
+    if (kind == D2D_KIND_WALL) {
+        const float2 i = normalize2(make_float2(b.x - a.x, b.y - a.y), l);
+        const float c2 = 2.0f * (i.x * w1.x + i.y * w1.y);
+        const float ex = r.x - (i.x - c2 * w1.x);
+        const float ey = r.y - (i.y - c2 * w1.y);
+        return ex * ex + ey * ey;
+    }
+    const float mx = -r.x, my = -r.y;
+    const float sin_a = mx * w1.y - my * w1.x;
+    const float cos_a = mx * w1.x + my * w1.y;
+    const float ds = sin_a - sc.x, dc = cos_a - sc.y;
+    return ds * ds + dc * dc;
+}
+
+// Wall.cartesian_to_parametric — geometry.py:589-598
+__device__ __forceinline__ float to_parametric(const float2 x, const float4 w0, const float4 w1) {
+    const float ox = x.x - w0.x, oy = x.y - w0.y;
+    return (w0.z * ox + w0.w * oy) / w1.z;
+}
+
+// path_length — geometry.py:176-203
+template <int NP>
+__device__ __forceinline__ float path_length(const float2 (&X)[NP]) {
+    float total = 0.0f;
+#pragma unroll
+    for (int i = 0; i + 1 < NP; ++i) {
+        const float dx = (X[i + 1].x - X[i].x) + kEps32;
+        const float dy = (X[i + 1].y - X[i].y) + kEps32;
+        const float len = sqrtf(dx * dx + dy * dy);
+        total = (i == 0) ? len : total + len;
+    }
+    return total;
+}
+
+// Exact pre-activation of one segment/object test — geometry.py:153-173 with tol = 0.005
+__device__ __forceinline__ float hit_exact(const float a, const float b, const float d) {
+    if (d == 0.0f) return -CUDART_INF_F;  // t = +inf  ->  (1+tol) - inf
+    const float ta = a / d, tb = b / d;
+    const float h = fminf(fminf(ta + kTolSeg, kHiSeg - ta), fminf(tb + kTolSeg, kHiSeg - tb));
+    // fminf drops NaNs; a NaN parameter makes every comparison false in the reference
+    return (ta != ta || tb != tb) ? -CUDART_INF_F : h;
+}
+
+// ---- candidate odometer (lexicographic, no equal neighbours) over positions in `allowed` ------
+template <int K>
+struct Odometer {
+    int pos[K > 0 ? K : 1];
+    __device__ __forceinline__ bool first(int m) {
+        if (K == 0) return true;
+        if (m <= 0 || (K > 1 && m < 2)) return false;
+#pragma unroll
+        for (int i = 0; i < K; ++i) pos[i] = (i & 1);  // 0,1,0,1,...
+        return true;
+    }
+    __device__ __forceinline__ bool next(int m) {
+        if (K == 0) return false;
+#pragma unroll
+        for (int i = K - 1; i >= 0; --i) {
+            int v = pos[i] + 1;
+            if (i > 0 && v == pos[i - 1]) ++v;
+            if (v < m) {
+                pos[i] = v;
+#pragma unroll
+                for (int j = i + 1; j < K; ++j) pos[j] = (pos[j - 1] == 0) ? 1 : 0;
+                return true;
+            }
+        }
+        return false;
+    }
+};
+
+}  // namespace d2d

@@ -1,0 +1,117 @@
+// differt2d_b200 — path construction dispatch and the in-register Adam solver of FermatPath / MinPath.
+//
+// FermatPath.from_tx_objects_rx  geometry.py:1121-1204 : minimise path_length over the parametric
+//                                coordinates of the interacting objects;
+// MinPath.from_tx_objects_rx     geometry.py:1211-1288 : minimise the sum of interaction residuals;
+// both through optimize.minimize (optimize.py:44-97): `steps` iterations of optax.adam(lr) started
+// at x0 (optimize.py:132), whole state (theta, mu, nu : <= 3*K floats) in registers.
+#pragma once
+
+#include "d2d_adjoint.cuh"
+#include "d2d_trace.cuh"
+
+namespace d2d {
+
+// parametric_to_cartesian — geometry.py:976-1010, Wall :581-587, Vertex :383-389
+template <int K>
+__device__ __forceinline__ void place_points(const SceneTab& T, const Cand<K>& cd, const float (&th)[K > 0 ? K : 1],
+                                             float2 (&X)[K + 2]) {
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const float4 w0 = T.w0[cd.c[i]];
+        if (T.kind[cd.c[i]] == D2D_KIND_VERTEX) X[i + 1] = make_float2(w0.x, w0.y);
+        else X[i + 1] = make_float2(w0.x + th[i] * w0.z, w0.y + th[i] * w0.w);
+    }
+}
+
+// loss_fun value and gradient w.r.t. the interior points X[1..K]
+template <int METHOD, int K>
+__device__ __forceinline__ float solver_loss_grad(const SceneTab& T, const Cand<K>& cd, const float2 (&X)[K + 2],
+                                                  float2 (&G)[K + 2]) {
+#pragma unroll
+    for (int i = 0; i < K + 2; ++i) G[i] = make_float2(0.f, 0.f);
+    if (METHOD == D2D_METHOD_FERMAT) {
+        float total = 0.0f;
+#pragma unroll
+        for (int i = 0; i <= K; ++i) {  // path_length geometry.py:176-203
+            const float dx = (X[i + 1].x - X[i].x) + kEps32;
+            const float dy = (X[i + 1].y - X[i].y) + kEps32;
+            const float len = sqrtf(dx * dx + dy * dy);
+            total = (i == 0) ? len : total + len;
+            const float inv = 1.0f / len;
+            G[i + 1].x += dx * inv; G[i + 1].y += dy * inv;
+            G[i].x -= dx * inv; G[i].y -= dy * inv;
+        }
+        return total;
+    }
+    float loss = 0.0f;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const int j = cd.c[i];
+        loss = loss + residual(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j]);
+        float2 nb = make_float2(0.f, 0.f);
+        float pb = 0.f;
+        residual_adj(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j], 1.0f, G[i], G[i + 1], G[i + 2], nb, pb);
+    }
+    return loss;
+}
+
+template <int METHOD, int K>
+__device__ __forceinline__ void construct_path(const SceneTab& T, const KParams& p, const Cand<K>& cd,
+                                               const float2 tx, const float2 rx, const long long col,
+                                               float2 (&X)[K + 2], float& loss) {
+    if (METHOD == D2D_METHOD_IMAGE || K == 0) {
+        image_path<K>(T, cd, tx, rx, X);
+        loss = path_loss<K>(T, cd, X);
+        return;
+    }
+    constexpr int KK = K > 0 ? K : 1;
+    float th[KK], mu[KK], nu[KK];
+    {
+        int u = 0;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            mu[i] = 0.f;
+            nu[i] = 0.f;
+            th[i] = 0.f;
+            if (T.kind[cd.c[i]] != D2D_KIND_VERTEX) {
+                th[i] = p.x0 ? p.x0[col * p.max_order + u] : 0.5f;
+                ++u;
+            }
+        }
+    }
+    X[0] = tx;
+    X[K + 1] = rx;
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;  // optax.adam defaults
+    float b1p = 1.0f, b2p = 1.0f;
+    float last = 0.0f;
+    for (int s = 0; s < p.steps; ++s) {
+        place_points<K>(T, cd, th, X);
+        float2 G[K + 2];
+        last = solver_loss_grad<METHOD, K>(T, cd, X, G);
+        b1p *= b1;
+        b2p *= b2;
+        const float bc1 = 1.0f - b1p, bc2 = 1.0f - b2p;
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            if (T.kind[cd.c[i]] == D2D_KIND_VERTEX) continue;
+            const float4 w0 = T.w0[cd.c[i]];
+            const float g = G[i + 1].x * w0.z + G[i + 1].y * w0.w;
+            mu[i] = (1.0f - b1) * g + b1 * mu[i];
+            nu[i] = (1.0f - b2) * (g * g) + b2 * nu[i];
+            const float mh = mu[i] / bc1, nh = nu[i] / bc2;
+            th[i] = th[i] + (-p.lr) * (mh / (sqrtf(nh) + eps));
+        }
+    }
+    place_points<K>(T, cd, th, X);
+    if (METHOD == D2D_METHOD_FERMAT) loss = path_loss<K>(T, cd, X);  // geometry.py:1202-1204
+    else {
+        if (p.steps <= 0) {
+            float2 G[K + 2];
+            last = solver_loss_grad<METHOD, K>(T, cd, X, G);
+        }
+        loss = last;  // optimize.py:96-97 losses[-1]
+    }
+}
+
+}  // namespace d2d

@@ -1,0 +1,252 @@
+"""
+Array-level entry points over the C ABI (the analogue of the `jax.ffi` custom calls wrapped in
+`jax.custom_vjp` described in INTEGRATION.md).  torch supplies device buffers, the current CUDA
+stream and the autograd graph node; every numerical step happens in libdiffert2d_b200.so.
+"""
+
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib as L
+from .defaults import DEFAULT_ALPHA, DEFAULT_HEIGHT, DEFAULT_PATCH, DEFAULT_R_COEF
+
+MODES = {"hard": L.MODE_HARD, "hard_sigmoid": L.MODE_HARD_SIGMOID, "sigmoid": L.MODE_SIGMOID}
+METHODS = {"image": L.METHOD_IMAGE, "fermat": L.METHOD_FERMAT, "minpath": L.METHOD_MINPATH}
+FUNS = {"received_power": L.FUN_RECEIVED_POWER, "length_squared": L.FUN_LENGTH_SQUARED}
+ROLES = {"receivers": L.GRID_RECEIVERS, "transmitters": L.GRID_TRANSMITTERS}
+
+
+@dataclass(frozen=True)
+class TraceConfig:
+    """Static configuration of one call (what would be FFI attributes / the XLA compile-cache key)."""
+
+    grid_role: str = "receivers"
+    min_order: int = 0
+    max_order: int = 1
+    filter_nodes: tuple = ()
+    method: str = "image"
+    steps: int = 100
+    lr: float = 0.1
+    mode: str = "hard"
+    tol: float = 1e-2
+    patch: float = DEFAULT_PATCH
+    fun: str = "received_power"
+    r_coef: float = DEFAULT_R_COEF
+    height: float = DEFAULT_HEIGHT
+    reduce_all: bool = False
+
+
+def _dev_f32(x, device) -> torch.Tensor:
+    t = x if isinstance(x, torch.Tensor) else torch.as_tensor(np.asarray(x, dtype=np.float32))
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _require_cuda(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise L.D2DError("differt2d_b200 computes on CUDA devices only (no CPU fallback); got device " + str(device))
+
+
+class _Packed:
+    """Keeps every buffer referenced by a D2DProblem alive for the duration of a call."""
+
+    def __init__(self, cfg: TraceConfig, xys, kinds, phis, fixed, grid, alpha, x0, device):
+        _require_cuda(device)
+        self.device = device
+        self.cfg = cfg
+        self.xys = _dev_f32(xys, device).reshape(-1, 2, 2)
+        n = self.xys.shape[0]
+        self.kinds = None
+        if kinds is not None:
+            k = kinds if isinstance(kinds, torch.Tensor) else torch.as_tensor(np.asarray(kinds, dtype=np.uint8))
+            self.kinds = k.to(device=device, dtype=torch.uint8).contiguous()
+            assert self.kinds.numel() == n
+        self.phis = None if phis is None else _dev_f32(phis, device).reshape(n)
+        self.fixed = _dev_f32(fixed, device).reshape(-1, 2)
+        self.grid = _dev_f32(grid, device).reshape(-1, 2)
+        self.x0 = None if x0 is None else _dev_f32(x0, device)
+        self.alpha_t = None
+        alpha_f = DEFAULT_ALPHA
+        if isinstance(alpha, torch.Tensor):
+            self.alpha_t = alpha.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
+        else:
+            alpha_f = float(alpha)
+        self.filter = np.ascontiguousarray(np.asarray(cfg.filter_nodes, dtype=np.int32))
+        p = L.new_problem()
+        p.n_objects = n
+        p.objects_xys = self.xys.data_ptr()
+        p.object_kinds = self.kinds.data_ptr() if self.kinds is not None else None
+        p.object_phis = self.phis.data_ptr() if self.phis is not None else None
+        p.n_fixed = self.fixed.shape[0]
+        p.fixed_xy = self.fixed.data_ptr()
+        p.n_grid = self.grid.shape[0]
+        p.grid_xy = self.grid.data_ptr()
+        p.grid_role = ROLES[cfg.grid_role]
+        p.min_order, p.max_order = int(cfg.min_order), int(cfg.max_order)
+        p.filter_nodes = self.filter.ctypes.data if self.filter.size else None
+        p.n_filter = int(self.filter.size)
+        p.method = METHODS[cfg.method]
+        p.steps = int(cfg.steps)
+        p.lr = float(cfg.lr)
+        p.x0 = self.x0.data_ptr() if self.x0 is not None else None
+        p.mode = MODES[cfg.mode]
+        p.alpha = alpha_f
+        p.alpha_dev = self.alpha_t.data_ptr() if self.alpha_t is not None else None
+        p.tol = float(cfg.tol)
+        p.patch = float(cfg.patch)
+        p.fun = FUNS[cfg.fun]
+        p.r_coef = float(cfg.r_coef)
+        p.height = float(cfg.height)
+        p.reduce_all = int(cfg.reduce_all)
+        self.p = p
+        self.T = self.fixed.shape[0]
+        self.R = self.grid.shape[0]
+        self.N = n
+
+    @property
+    def num_candidates(self) -> int:
+        c = L.lib().d2d_problem_num_candidates(C.byref(self.p))
+        if c < 0:
+            raise L.D2DError("invalid problem: " + L.lib().d2d_last_error().decode())
+        return int(c)
+
+    def z_shape(self):
+        return (self.R,) if self.cfg.reduce_all else (self.T, self.R)
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def power_fwd(cfg: TraceConfig, xys, fixed, grid, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA, x0=None,
+              want_valid: bool = False, device=None):
+    """Z [T,R] (or [R]); with want_valid also the validity of every (fixed, grid point, candidate)."""
+    device = torch.device(device) if device is not None else (
+        grid.device if isinstance(grid, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
+    pk = _Packed(cfg, xys, kinds, phis, fixed, grid, alpha, x0, device)
+    with torch.cuda.device(device):
+        Z = torch.empty(pk.z_shape(), dtype=torch.float32, device=device)
+        valid = None
+        if want_valid:
+            valid = torch.empty((pk.T, pk.R, pk.num_candidates), dtype=torch.float32, device=device)
+        rc = L.lib().d2d_power_fwd(C.byref(pk.p), Z.data_ptr(), valid.data_ptr() if want_valid else None, _stream(device))
+        L.check(rc, "d2d_power_fwd")
+    return (Z, valid) if want_valid else Z
+
+
+def power_bwd(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA, x0=None,
+              want=("Z", "grid", "objects", "phis", "fixed", "alpha"), device=None) -> dict:
+    """Recompute-based VJP; returns a dict with the requested cotangents (and Z for value_and_grad)."""
+    device = torch.device(device) if device is not None else (
+        grid.device if isinstance(grid, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
+    pk = _Packed(cfg, xys, kinds, phis, fixed, grid, alpha, x0, device)
+    with torch.cuda.device(device):
+        zb = None
+        if Zbar is not None:
+            zb = _dev_f32(Zbar, device).reshape(pk.z_shape())
+        out = {}
+        if "Z" in want:
+            out["Z"] = torch.empty(pk.z_shape(), dtype=torch.float32, device=device)
+        if "grid" in want:
+            out["grid"] = torch.empty((*pk.z_shape(), 2), dtype=torch.float32, device=device)
+        if "objects" in want:
+            out["objects"] = torch.empty((pk.N, 2, 2), dtype=torch.float32, device=device)
+        if "phis" in want:
+            out["phis"] = torch.empty((pk.N,), dtype=torch.float32, device=device)
+        if "fixed" in want:
+            out["fixed"] = torch.empty((pk.T, 2), dtype=torch.float32, device=device)
+        if "alpha" in want:
+            out["alpha"] = torch.empty((1,), dtype=torch.float32, device=device)
+        ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
+        rc = L.lib().d2d_power_bwd(C.byref(pk.p), zb.data_ptr() if zb is not None else None, ptr("Z"), ptr("grid"),
+                                   ptr("objects"), ptr("phis"), ptr("fixed"), ptr("alpha"), _stream(device))
+        L.check(rc, "d2d_power_bwd")
+    return out
+
+
+class _PowerMap(torch.autograd.Function):
+    """custom_vjp analogue: residuals are the inputs only; the backward re-traces (no stored activations)."""
+
+    @staticmethod
+    def forward(ctx, xys, phis, fixed, grid, alpha, cfg, kinds, x0):
+        ctx.cfg, ctx.kinds, ctx.x0 = cfg, kinds, x0
+        ctx.save_for_backward(xys, phis, fixed, grid, alpha)
+        return power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, device=grid.device)
+
+    @staticmethod
+    def backward(ctx, Zbar):
+        xys, phis, fixed, grid, alpha = ctx.saved_tensors
+        need = ctx.needs_input_grad
+        want = [w for w, n in zip(("objects", "phis", "fixed", "grid", "alpha"), need[:5]) if n]
+        if ctx.cfg.reduce_all or fixed.shape[0] == 1:
+            g = power_bwd(ctx.cfg, xys, fixed, grid, Zbar.contiguous(), kinds=ctx.kinds, phis=phis, alpha=alpha,
+                          x0=ctx.x0, want=tuple(want), device=grid.device)
+            gg = g.get("grid")
+            if gg is not None:
+                gg = gg.reshape(-1, 2) if ctx.cfg.reduce_all else gg.sum(dim=0)
+        else:
+            g = power_bwd(ctx.cfg, xys, fixed, grid, Zbar.contiguous(), kinds=ctx.kinds, phis=phis, alpha=alpha,
+                          x0=ctx.x0, want=tuple(want), device=grid.device)
+            gg = g.get("grid")
+            if gg is not None:
+                gg = gg.sum(dim=0)
+        return (
+            g["objects"].reshape(xys.shape) if "objects" in g else None,
+            g["phis"].reshape(phis.shape) if "phis" in g else None,
+            g["fixed"].reshape(fixed.shape) if "fixed" in g else None,
+            gg.reshape(grid.shape) if gg is not None else None,
+            g["alpha"].reshape(alpha.shape) if "alpha" in g else None,
+            None, None, None,
+        )
+
+
+def power_map(xys: torch.Tensor, fixed: torch.Tensor, grid: torch.Tensor, *, cfg: TraceConfig,
+              phis: Optional[torch.Tensor] = None, alpha=DEFAULT_ALPHA, kinds=None, x0=None) -> torch.Tensor:
+    """
+    Differentiable power map: Z = f(object vertices, RIS angles, fixed points, grid points, alpha).
+    ``torch.autograd`` over it plays the role of ``jax.grad`` over
+    ``Scene.accumulate_on_*_grid_over_paths`` in the reference.
+    """
+    dev = grid.device
+    _require_cuda(dev)
+    xys = xys.to(dev, torch.float32)
+    n = xys.reshape(-1, 2, 2).shape[0]
+    phis_t = torch.zeros(n, device=dev) if phis is None else phis.to(dev, torch.float32)
+    alpha_t = alpha if isinstance(alpha, torch.Tensor) else torch.tensor(float(alpha), device=dev)
+    alpha_t = alpha_t.to(dev, torch.float32)
+    return _PowerMap.apply(xys, phis_t, fixed.to(dev, torch.float32), grid.to(dev, torch.float32), alpha_t, cfg,
+                           kinds, x0)
+
+
+def candidates(n_objects: int, order: int, filter_nodes: Sequence[int] = (), *, device=None) -> np.ndarray:
+    """
+    [count, order] int32 list of one order — scene.py:122-175.  With ``device`` (a CUDA device) the
+    list is produced by the integer decode kernel, otherwise by the host odometer of the same library.
+    """
+    f = np.ascontiguousarray(np.asarray(filter_nodes, dtype=np.int32))
+    fp = f.ctypes.data if f.size else None
+    cnt = L.lib().d2d_candidates_count(n_objects, order, fp, int(f.size))
+    if cnt < 0:
+        raise L.D2DError("d2d_candidates_count: invalid arguments")
+    if device is not None:
+        dev = torch.device(device)
+        _require_cuda(dev)
+        with torch.cuda.device(dev):
+            out = torch.empty((cnt, order), dtype=torch.int32, device=dev)
+            rc = L.lib().d2d_candidates_device(n_objects, order, fp, int(f.size), out.data_ptr() if cnt * order else None,
+                                               _stream(dev))
+            L.check(rc, "d2d_candidates_device")
+        return out.cpu().numpy()
+    out = np.empty((cnt, order), dtype=np.int32)
+    rc = L.lib().d2d_candidates_host(n_objects, order, fp, int(f.size), out.ctypes.data if out.size else None)
+    L.check(rc, "d2d_candidates_host")
+    return out
+
+
+def launch_count() -> int:
+    return int(L.lib().d2d_launch_count())

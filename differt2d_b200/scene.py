@@ -1,0 +1,338 @@
+"""
+Host-side mirror of differt2d/scene.py for the hot path: the `Scene` container, its canned
+builders (used as input generators), `all_path_candidates`, and the three accumulation entry
+points with the reference's names, keywords, return structure and iteration order —
+
+    Scene.accumulate_on_receivers_grid_over_paths      scene.py:1803-1953
+    Scene.accumulate_on_transmitters_grid_over_paths   scene.py:1489-1648
+    Scene.accumulate_over_paths                        scene.py:1272-1334
+
+Arrays in, arrays out: `X`, `Y` may be torch tensors (CUDA: zero-copy; CPU: staged) or numpy
+arrays; results come back in the same container type, float32, shaped like `X` (+ a trailing 2 for
+gradients), exactly as the reference returns them.  Everything numerical runs in the CUDA library.
+"""
+
+from __future__ import annotations
+
+import json
+from typing import Any, Callable, Iterator, Mapping, Optional, Sequence, Union
+
+import numpy as np
+import torch
+
+from . import functional as F
+from . import utils
+from .defaults import DEFAULT_ALPHA, DEFAULT_HEIGHT, DEFAULT_PATCH, DEFAULT_R_COEF
+from .geometry import RIS, FermatPath, ImagePath, MinPath, Path, Point, Vertex, Wall
+from .logic import resolve_mode
+
+
+def _resolve_fun(fun, fun_args, fun_kwargs):
+    fun_kwargs = dict(fun_kwargs or {})
+    if fun_args:
+        raise NotImplementedError("positional fun_args are not supported by the fused kernels; use fun_kwargs")
+    if fun is utils.received_power or fun == "received_power":
+        r_coef = float(fun_kwargs.pop("r_coef", DEFAULT_R_COEF))
+        height = float(fun_kwargs.pop("height", DEFAULT_HEIGHT))
+        if fun_kwargs:
+            raise TypeError(f"unexpected fun_kwargs for received_power: {sorted(fun_kwargs)}")
+        return "received_power", r_coef, height
+    if fun is utils.length_squared or fun == "length_squared":
+        return "length_squared", DEFAULT_R_COEF, DEFAULT_HEIGHT
+    raise NotImplementedError(
+        "the fused kernels implement fun in {utils.received_power, utils.length_squared}; an arbitrary "
+        "Python `fun` (scene.py:51) needs the generic escape hatch listed under DESIGN.md 'next'"
+    )
+
+
+def _default_device():
+    if not torch.cuda.is_available():
+        raise F.L.D2DError("no CUDA device: differt2d_b200 has no CPU fallback")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+class Scene:
+    """scene.py:178-192 — transmitters / receivers by name (insertion order kept) and a list of objects."""
+
+    def __init__(self, transmitters: Optional[Mapping[str, Point]] = None,
+                 receivers: Optional[Mapping[str, Point]] = None, objects: Sequence[Any] = ()):
+        self.transmitters = dict(transmitters or {})
+        self.receivers = dict(receivers or {})
+        self.objects = list(objects)
+
+    # ---- mutators (scene.py:194-426), functional style -------------------------------------------
+    def with_transmitters(self, **tx: Point) -> "Scene":
+        return Scene(tx, self.receivers, self.objects)
+
+    def with_receivers(self, **rx: Point) -> "Scene":
+        return Scene(self.transmitters, rx, self.objects)
+
+    def with_objects(self, *objects) -> "Scene":
+        return Scene(self.transmitters, self.receivers, objects)
+
+    def add_objects(self, *objects) -> "Scene":
+        return Scene(self.transmitters, self.receivers, [*self.objects, *objects])
+
+    def update_transmitters(self, **tx: Point) -> "Scene":
+        return Scene({**self.transmitters, **tx}, self.receivers, self.objects)
+
+    def update_receivers(self, **rx: Point) -> "Scene":
+        return Scene(self.transmitters, {**self.receivers, **rx}, self.objects)
+
+    # ---- canned scenes (scene.py:670-935): input generators --------------------------------------
+    @classmethod
+    def from_walls_array(cls, walls) -> "Scene":  # scene.py:670-693
+        walls = np.asarray(walls, dtype=np.float32).reshape(-1, 2, 2)
+        return cls(objects=[Wall(xys=w) for w in walls])
+
+    @classmethod
+    def square_scene(cls, tx_coords=(0.2, 0.2), rx_coords=(0.5, 0.6)) -> "Scene":  # scene.py:790-836
+        walls = [[[0, 0], [1, 0]], [[1, 0], [1, 1]], [[1, 1], [0, 1]], [[0, 1], [0, 0]]]
+        return cls({"tx": Point(xy=tx_coords)}, {"rx": Point(xy=rx_coords)}, [Wall(xys=w) for w in walls])
+
+    @classmethod
+    def square_scene_with_wall(cls, ratio=0.6, tx_coords=(0.2, 0.5), rx_coords=(0.8, 0.5)) -> "Scene":  # :839-882
+        s = cls.square_scene(tx_coords, rx_coords)
+        return s.add_objects(Wall(xys=[[0.5, 0.5 * (1 - ratio)], [0.5, 0.5 * (1 + ratio)]]))
+
+    @classmethod
+    def square_scene_with_obstacle(cls, ratio=0.1, **kwargs) -> "Scene":  # scene.py:885-935
+        s = cls.square_scene(**kwargs)
+        hl = 0.5 * ratio
+        x0, x1, y0, y1 = 0.5 - hl, 0.5 + hl, 0.5 - hl, 0.5 + hl
+        return s.add_objects(Wall(xys=[[x0, y0], [x1, y0]]), Wall(xys=[[x1, y0], [x1, y1]]),
+                             Wall(xys=[[x1, y1], [x0, y1]]), Wall(xys=[[x0, y1], [x0, y0]]))
+
+    @classmethod
+    def basic_scene(cls, tx_coords=(0.1, 0.1), rx_coords=(0.302, 0.2147)) -> "Scene":  # scene.py:736-787
+        s = cls.square_scene(tx_coords, rx_coords)
+        return s.add_objects(Wall(xys=[[0.4, 0.0], [0.4, 0.4]]), Wall(xys=[[0.4, 0.4], [0.3, 0.4]]),
+                             Wall(xys=[[0.1, 0.4], [0.0, 0.4]]))
+
+    @classmethod
+    def random_uniform_scene(cls, *, key, n_transmitters=1, n_walls=1, n_receivers=1) -> "Scene":
+        """scene.py:696-733 layout; ``key`` seeds numpy's Generator (the JAX key stream is not reproduced)."""
+        rng = np.random.default_rng(key)
+        pts = rng.random((n_transmitters + 2 * n_walls + n_receivers, 2), dtype=np.float32)
+        tx = {f"tx_{i}": Point(xy=pts[i]) for i in range(n_transmitters)}
+        rx = {f"rx_{i}": Point(xy=pts[-(i + 1)]) for i in range(n_receivers)}
+        walls = [Wall(xys=pts[2 * i + n_transmitters: 2 * i + 2 + n_transmitters]) for i in range(n_walls)]
+        return cls(tx, rx, walls)
+
+    @classmethod
+    def from_geojson(cls, s_or_fp, tx_loc="NW", rx_loc="SE") -> "Scene":
+        """scene.py:428-668 — one Wall per (coords[i-1], coords[i]) of every Polygon's outer ring."""
+        if hasattr(s_or_fp, "read"):
+            s_or_fp = s_or_fp.read()
+        d = json.loads(s_or_fp)
+        walls = []
+        for feat in d.get("features", []):
+            geom = feat.get("geometry")
+            if geom and geom["type"] == "Polygon":
+                coords = geom["coordinates"][0]
+                for i in range(len(coords)):
+                    walls.append(Wall(xys=np.asarray([coords[i - 1], coords[i]], dtype=np.float64).astype(np.float32)))
+        sc = cls(objects=walls)
+        if walls:
+            return sc.with_transmitters(tx=Point(xy=sc.get_location(tx_loc))).with_receivers(
+                rx=Point(xy=Scene(objects=walls).get_location(rx_loc)))
+        return sc.with_transmitters(tx=Point(xy=[0.0, 0.0])).with_receivers(rx=Point(xy=[1.0, 1.0]))
+
+    # ---- Plottable pieces needed to build inputs (abc.py:30-126, scene.py:1023-1036) --------------
+    def bounding_box(self) -> np.ndarray:
+        boxes = [p.bounding_box() for p in self.transmitters.values()]
+        boxes += [p.bounding_box() for p in self.receivers.values()]
+        boxes += [o.bounding_box() for o in self.objects]
+        b = np.stack(boxes)
+        return np.vstack([b[:, 0].min(axis=0), b[:, 1].max(axis=0)]).astype(np.float32)
+
+    def grid(self, m: int = 50, n: Optional[int] = None):
+        """abc.py:59-81 — (X, Y) of shape (n, m) over the bounding box."""
+        bb = self.bounding_box()
+        n = m if n is None else n
+        x = np.linspace(bb[0, 0], bb[1, 0], m, dtype=np.float32)
+        y = np.linspace(bb[0, 1], bb[1, 1], n, dtype=np.float32)
+        return np.meshgrid(x, y)
+
+    def center(self) -> np.ndarray:
+        bb = self.bounding_box()
+        return (np.float32(0.5) * (bb[0] + bb[1])).astype(np.float32)
+
+    def get_location(self, location: str) -> np.ndarray:  # abc.py:95-126
+        (xmin, ymin), (xmax, ymax) = self.bounding_box()
+        xavg, yavg = np.float32(0.5) * (xmin + xmax), np.float32(0.5) * (ymin + ymax)
+        x, y = {"N": (xavg, ymax), "E": (xmax, yavg), "S": (xavg, ymin), "W": (xmin, yavg), "C": (xavg, yavg),
+                "NE": (xmax, ymax), "NW": (xmin, ymax), "SE": (xmax, ymin), "SW": (xmin, ymin)}[location]
+        return np.array([x, y], dtype=np.float32)
+
+    # ---- packing ----------------------------------------------------------------------------------
+    def packed_objects(self):
+        """objects as arrays: xys [N,2,2] f32, kinds [N] u8, phis [N] f32."""
+        n = len(self.objects)
+        xys = np.zeros((n, 2, 2), np.float32)
+        kinds = np.zeros(n, np.uint8)
+        phis = np.zeros(n, np.float32)
+        for i, o in enumerate(self.objects):
+            if not isinstance(o, (Wall, Vertex)):
+                raise NotImplementedError(f"object type {type(o).__name__}: the kernels support Wall, RIS and Vertex")
+            xys[i] = o.packed_xys()
+            kinds[i] = o.KIND
+            if isinstance(o, RIS):
+                phis[i] = o.phi
+        return xys, kinds, phis
+
+    def all_transmitter_receiver_pairs(self):  # scene.py:1072-1087
+        for tx in self.transmitters.items():
+            for rx in self.receivers.items():
+                yield tx, rx
+
+    # ---- candidates (scene.py:1089-1134) ------------------------------------------------------------
+    def _filter_nodes(self, filter_objects) -> tuple:
+        if filter_objects is None:
+            return ()
+        return tuple(i for i, o in enumerate(self.objects) if not filter_objects(o))
+
+    def all_path_candidates(self, min_order: int = 0, max_order: int = 1, *, order: Optional[int] = None,
+                            filter_objects: Optional[Callable[[Any], bool]] = None, device=None) -> list:
+        """List with one int32 array (shape (k,)) per candidate, orders ascending, lexicographic inside."""
+        if order is not None:
+            min_order = max_order = order
+        fn = self._filter_nodes(filter_objects)
+        if device is None and torch.cuda.is_available():
+            device = _default_device()
+        out = []
+        for k in range(min_order, max_order + 1):
+            out.extend(list(F.candidates(len(self.objects), k, fn, device=device)))
+        return out
+
+    # ---- accumulation -------------------------------------------------------------------------------
+    def _config(self, grid_role, fun, fun_args, fun_kwargs, reduce_all, path_cls, path_cls_kwargs, min_order,
+                max_order, order, filter_objects, kwargs):
+        kwargs = dict(kwargs)
+        if order is not None:
+            min_order = max_order = order
+        method = getattr(path_cls, "METHOD", None)
+        if method is None:
+            raise NotImplementedError("path_cls must be ImagePath, FermatPath or MinPath")
+        pk = dict(path_cls_kwargs or {})
+        steps = int(pk.pop("steps", 100))
+        many = int(pk.pop("many", 1))
+        if many != 1:
+            raise NotImplementedError("many > 1 restarts (optimize.py:171-182) are listed under DESIGN.md 'next'")
+        optimizer = pk.pop("optimizer", None)
+        if optimizer is not None or pk:
+            raise NotImplementedError(f"unsupported path_cls_kwargs: {sorted(pk) + (['optimizer'] if optimizer else [])}")
+        mode = resolve_mode(kwargs.pop("approx", None), kwargs.pop("function", None))
+        alpha = kwargs.pop("alpha", DEFAULT_ALPHA)
+        tol = float(kwargs.pop("tol", 1e-2))
+        patch = float(kwargs.pop("patch", DEFAULT_PATCH))
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        fname, r_coef, height = _resolve_fun(fun, fun_args, fun_kwargs)
+        if method == "image" and any(isinstance(o, Vertex) for i, o in enumerate(self.objects)
+                                     if i not in self._filter_nodes(filter_objects)):
+            raise TypeError("ImagePath cannot interact with Vertex objects (geometry.py:1020 expects walls)")
+        cfg = F.TraceConfig(grid_role=grid_role, min_order=min_order, max_order=max_order,
+                            filter_nodes=self._filter_nodes(filter_objects), method=method, steps=steps, lr=0.1,
+                            mode=mode, tol=tol, patch=patch, fun=fname, r_coef=r_coef, height=height,
+                            reduce_all=bool(reduce_all))
+        return cfg, alpha
+
+    def _x0(self, cfg: F.TraceConfig, key, device):
+        """Initial guesses per candidate (optimize.py:132); `key` is an int seed or an explicit [C,max_order] table."""
+        if cfg.method == "image" or cfg.max_order == 0:
+            return None
+        n_allowed = len(self.objects) - len(cfg.filter_nodes)
+        C = sum(F.L.lib().d2d_candidates_count(len(self.objects), k, None, 0) if not cfg.filter_nodes else
+                len(F.candidates(len(self.objects), k, cfg.filter_nodes)) for k in range(cfg.min_order, cfg.max_order + 1))
+        del n_allowed
+        if key is None:
+            raise TypeError("FermatPath / MinPath need `key` (an int seed or an explicit x0 table)")
+        if isinstance(key, (int, np.integer)):
+            return np.random.default_rng(int(key)).random((C, cfg.max_order), dtype=np.float32)
+        x0 = np.asarray(key.detach().cpu() if hasattr(key, "detach") else key, dtype=np.float32)
+        if x0.shape != (C, cfg.max_order):
+            raise ValueError(f"x0 table must have shape {(C, cfg.max_order)}, got {x0.shape}")
+        return x0
+
+    def _grid_call(self, grid_role, X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad, path_cls,
+                   path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs):
+        cfg, alpha = self._config(grid_role, fun, fun_args, fun_kwargs, reduce_all, path_cls, path_cls_kwargs,
+                                  min_order, max_order, order, filter_objects, kwargs)
+        as_numpy = not isinstance(X, torch.Tensor)
+        Xt = torch.as_tensor(np.asarray(X, dtype=np.float32)) if as_numpy else X
+        Yt = torch.as_tensor(np.asarray(Y, dtype=np.float32)) if as_numpy else Y
+        device = Xt.device if Xt.device.type == "cuda" else _default_device()
+        shape = tuple(Xt.shape)
+        grid = torch.stack((Xt.to(device, torch.float32), Yt.to(device, torch.float32)), dim=-1).reshape(-1, 2)  # dstack
+        fixed_src = self.transmitters if grid_role == "receivers" else self.receivers
+        names = list(fixed_src.keys())
+        fixed = np.stack([fixed_src[k].xy for k in names]) if names else np.zeros((0, 2), np.float32)
+        xys, kinds, phis = self.packed_objects()
+        x0 = self._x0(cfg, key, device)
+        back = (lambda t: t.cpu().numpy()) if as_numpy else (lambda t: t.to(Xt.device))
+        want_grad = grad or value_and_grad
+        if not want_grad:
+            Z = F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, device=device)
+            if reduce_all:
+                return back(Z.reshape(shape))
+            return ((k, back(Z[i].reshape(shape))) for i, k in enumerate(names))
+        out = F.power_bwd(cfg, xys, fixed, grid, None, kinds=kinds, phis=phis, alpha=alpha, x0=x0,
+                          want=("Z", "grid"), device=device)
+        Z, dZ = out["Z"], out["grid"]
+        if reduce_all:
+            Z, dZ = back(Z.reshape(shape)), back(dZ.reshape(*shape, 2))
+            return (Z, dZ) if value_and_grad else dZ
+        if value_and_grad:  # scene.py:1920-1923 value_and_grad overrides grad
+            return ((k, (back(Z[i].reshape(shape)), back(dZ[i].reshape(*shape, 2)))) for i, k in enumerate(names))
+        return ((k, back(dZ[i].reshape(*shape, 2))) for i, k in enumerate(names))
+
+    def accumulate_on_receivers_grid_over_paths(
+        self, X, Y, fun=utils.received_power, fun_args: tuple = (), fun_kwargs: Optional[Mapping[str, Any]] = None, *,
+        reduce_all: bool = False, grad: bool = False, value_and_grad: bool = False, path_cls: type = ImagePath,
+        path_cls_kwargs: Optional[Mapping[str, Any]] = None, receiver_cls: type = Point, min_order: int = 0,
+        max_order: int = 1, order: Optional[int] = None, filter_objects=None, key=None, **kwargs: Any,
+    ):
+        """scene.py:1803-1953 — per-transmitter maps over a grid of receivers, keyed by transmitter name."""
+        return self._grid_call("receivers", X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad,
+                               path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs)
+
+    def accumulate_on_transmitters_grid_over_paths(
+        self, X, Y, fun=utils.received_power, fun_args: tuple = (), fun_kwargs: Optional[Mapping[str, Any]] = None, *,
+        reduce_all: bool = False, grad: bool = False, value_and_grad: bool = False, path_cls: type = ImagePath,
+        path_cls_kwargs: Optional[Mapping[str, Any]] = None, transmitter_cls: type = Point, min_order: int = 0,
+        max_order: int = 1, order: Optional[int] = None, filter_objects=None, key=None, **kwargs: Any,
+    ):
+        """scene.py:1489-1648 — per-receiver maps over a grid of transmitters, keyed by receiver name."""
+        return self._grid_call("transmitters", X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad,
+                               path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs)
+
+    def accumulate_over_paths(self, fun=utils.received_power, fun_args: tuple = (),
+                              fun_kwargs: Optional[Mapping[str, Any]] = None, *, reduce_all: bool = False,
+                              path_cls: type = ImagePath, path_cls_kwargs=None, min_order: int = 0, max_order: int = 1,
+                              order: Optional[int] = None, filter_objects=None, key=None, **kwargs: Any):
+        """
+        scene.py:1272-1334 — point-to-point: (tx name, rx name, accumulated value) for every pair, or
+        their sum.  Runs as a receivers "grid" holding the scene's receivers.
+        NB the reference draws one PRNG key per (pair, candidate) here (scene.py:1209-1212); this mirror
+        uses the per-candidate table of the grid methods for every pair.
+        """
+        cfg, alpha = self._config("receivers", fun, fun_args, fun_kwargs, False, path_cls, path_cls_kwargs,
+                                  min_order, max_order, order, filter_objects, kwargs)
+        device = _default_device()
+        tx_names, rx_names = list(self.transmitters), list(self.receivers)
+        fixed = np.stack([self.transmitters[k].xy for k in tx_names]) if tx_names else np.zeros((0, 2), np.float32)
+        grid = np.stack([self.receivers[k].xy for k in rx_names]) if rx_names else np.zeros((0, 2), np.float32)
+        xys, kinds, phis = self.packed_objects()
+        x0 = self._x0(cfg, key, device)
+        if not tx_names or not rx_names:
+            return np.float32(0.0) if reduce_all else iter(())
+        Z = F.power_fwd(cfg, xys, fixed, torch.as_tensor(grid), kinds=kinds, phis=phis, alpha=alpha, x0=x0,
+                        device=device).cpu().numpy()
+        if reduce_all:
+            total = np.float32(0.0)
+            for i in range(len(tx_names)):
+                for j in range(len(rx_names)):
+                    total = np.float32(total + Z[i, j])
+            return total
+        return ((t, r, Z[i, j]) for i, t in enumerate(tx_names) for j, r in enumerate(rx_names))

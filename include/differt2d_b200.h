@@ -1,0 +1,161 @@
+/*
+ * differt2d_b200 — C ABI of the B200-native receiver-grid path-tracing hot path of DiffeRT2d.
+ *
+ * This header is the drop-in boundary.  The reference (pure Python on JAX) has no FFI of its
+ * own; what a maintainer would bind is a `jax.ffi` custom call per entry point below (see
+ * INTEGRATION.md for the XLA-FFI handler and the `jax.custom_vjp` wiring) replacing, on CUDA
+ * devices, the bodies of
+ *     Scene.accumulate_on_receivers_grid_over_paths      differt2d/scene.py:1803-1953
+ *     Scene.accumulate_on_transmitters_grid_over_paths   differt2d/scene.py:1489-1648
+ *     Scene.accumulate_over_paths (point-to-point)       differt2d/scene.py:1272-1334
+ *     all_path_candidates                                differt2d/scene.py:122-175
+ * Plain C types only: pointers, sizes, scalars.  Unless a comment says "host", every pointer is a
+ * DEVICE pointer owned by the caller; the library never allocates or frees device memory on these
+ * paths, launches asynchronously on the caller's stream, and never synchronises the device.
+ * All floating point is IEEE binary32, all indices int32 (scene.py:167).
+ *
+ * Error convention: every function returns 0 on success, a D2D_ERR_* code otherwise, and never
+ * throws; d2d_last_error() returns a thread-local message for the last failure.
+ */
+#ifndef DIFFERT2D_B200_H_
+#define DIFFERT2D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define D2D_ABI_VERSION 1
+
+/* limits of this build */
+#define D2D_MAX_ORDER 4      /* interactions per path (reference examples use <= 3) */
+#define D2D_MAX_OBJECTS 1024 /* scene objects (walls + RIS + vertices) */
+
+/* object kinds — geometry.py: Wall :540-680, RIS :683-721, Vertex :352-431 */
+#define D2D_KIND_WALL 0
+#define D2D_KIND_RIS 1
+#define D2D_KIND_VERTEX 2
+
+/* which end of the link the grid samples */
+#define D2D_GRID_RECEIVERS 0    /* scene.py:1803 — fixed points are transmitters */
+#define D2D_GRID_TRANSMITTERS 1 /* scene.py:1489 — fixed points are receivers    */
+
+/* path construction — geometry.py: ImagePath :1013-1114, FermatPath :1117-1204, MinPath :1207-1288 */
+#define D2D_METHOD_IMAGE 0
+#define D2D_METHOD_FERMAT 1
+#define D2D_METHOD_MINPATH 2
+
+/* logic.py:218-617 — `approx=False` is HARD; `approx=True` picks the activation `function` */
+#define D2D_MODE_HARD 0
+#define D2D_MODE_HARD_SIGMOID 1 /* logic.py:238-255, the default activation (logic.py:266) */
+#define D2D_MODE_SIGMOID 2      /* logic.py:218-235 */
+
+/* the accumulated path function `fun` */
+#define D2D_FUN_RECEIVED_POWER 0 /* utils.py:16-54 : r_coef**k / (height**2 + length**2) */
+#define D2D_FUN_LENGTH_SQUARED 1 /* tests/test_scene.py:444,488 : path.length()**2 */
+
+/* gradient semantics of masked branches (DESIGN.md "NaN semantics") */
+#define D2D_GRAD_CLEAN 0 /* masked / saturated branches have zero cotangent */
+
+#define D2D_OK 0
+#define D2D_ERR_INVALID_ARGUMENT 1
+#define D2D_ERR_UNSUPPORTED 2
+#define D2D_ERR_CUDA 3
+
+typedef struct D2DProblem {
+    /* ---- scene objects: Scene.objects (scene.py:178-192) ---------------------------------- */
+    int32_t n_objects;
+    const float *objects_xys;    /* [n_objects,2,2]; a Vertex stores its xy in both rows          */
+    const uint8_t *object_kinds; /* [n_objects] D2D_KIND_* or NULL (= all walls)                  */
+    const float *object_phis;    /* [n_objects] RIS reflection angle (geometry.py:692) or NULL    */
+    /* ---- link end points ------------------------------------------------------------------- */
+    int32_t n_fixed;       /* transmitters (receivers grid) or receivers (transmitters grid)      */
+    const float *fixed_xy; /* [n_fixed,2], in dictionary order (scene.py:1072-1087)               */
+    int64_t n_grid;        /* R = n*m grid points                                                 */
+    const float *grid_xy;  /* [R,2] = dstack((X,Y)).reshape(-1,2) (scene.py:1932), row-major n×m  */
+    int32_t grid_role;     /* D2D_GRID_*                                                          */
+    /* ---- candidates: all_path_candidates (scene.py:122-175) --------------------------------- */
+    int32_t min_order, max_order;
+    const int32_t *filter_nodes; /* HOST pointer: object indices never visited (scene.py:158-160) */
+    int32_t n_filter;
+    /* ---- path construction ------------------------------------------------------------------ */
+    int32_t method;  /* D2D_METHOD_*                                                              */
+    int32_t steps;   /* Adam iterations, optimize.py:49 (default 100)                             */
+    float lr;        /* Adam learning rate, optimize.py:83 (0.1)                                  */
+    const float *x0; /* [C,max_order] initial guesses per candidate (optimize.py:132), Fermat/Min */
+    /* ---- validity logic: Path.is_valid (geometry.py:908-963) --------------------------------- */
+    int32_t mode;           /* D2D_MODE_*                                                         */
+    float alpha;            /* activation slope (defaults.py:3); must be > 0                      */
+    const float *alpha_dev; /* optional device scalar overriding `alpha` (a traced jnp scalar)    */
+    float tol;              /* loss tolerance of is_valid (geometry.py:915), default 1e-2         */
+    float patch;            /* wall lengthening for the occlusion test (geometry.py:632-635)      */
+    /* ---- accumulated function --------------------------------------------------------------- */
+    int32_t fun;    /* D2D_FUN_*                                                                  */
+    float r_coef;   /* defaults.py:12                                                             */
+    float height;   /* defaults.py:15                                                             */
+    int32_t reduce_all; /* sum over the fixed points (scene.py:1939-1952)                          */
+    int32_t grad_mode;  /* D2D_GRAD_*                                                              */
+} D2DProblem;
+
+/* Fills a problem with the reference's defaults (defaults.py, geometry.py:915, optimize.py:49,83). */
+void d2d_problem_defaults(D2DProblem *p);
+
+/* ---- candidates (replaces differt_core.rt.CompleteGraph/DiGraph.all_paths at scene.py:154-174) -- */
+/* Number of candidates of exactly `order` interactions; -1 on invalid arguments.                    */
+int64_t d2d_candidates_count(int32_t n_objects, int32_t order, const int32_t *filter_nodes /*host*/,
+                             int32_t n_filter);
+/* Lexicographic list, row-major [count, order] int32, into HOST memory.                              */
+int d2d_candidates_host(int32_t n_objects, int32_t order, const int32_t *filter_nodes /*host*/,
+                        int32_t n_filter, int32_t *out /*host*/);
+/* Same list written by an integer CUDA kernel (closed-form index -> sequence decode) into DEVICE memory. */
+int d2d_candidates_device(int32_t n_objects, int32_t order, const int32_t *filter_nodes /*host*/,
+                          int32_t n_filter, int32_t *out /*device*/, void *stream);
+/* Total over [min_order, max_order] as used by a problem (= columns of `valid_out`). */
+int64_t d2d_problem_num_candidates(const D2DProblem *p);
+
+/*
+ * Forward map.  Z: [n_fixed, R] (or [R] when reduce_all), Z[t,r] = sum over candidates, in list
+ * order, of valid * fun (scene.py:1892-1918).  valid_out: optional [n_fixed, R, C] float32
+ * validity of every (fixed point, grid point, candidate) — 0/1 in hard mode — for parity runs.
+ */
+int d2d_power_fwd(const D2DProblem *p, float *Z, float *valid_out, void *stream);
+
+/*
+ * Reverse mode by recomputation (what jax.vjp of the forward yields).
+ * Zbar: cotangent of Z, same shape as Z, or NULL (= ones: jax.grad of the sum, scene.py:1920-1923).
+ * Every output is optional (NULL = not wanted) and is OVERWRITTEN:
+ *   Z_out        same shape as Z (fused value_and_grad)
+ *   grid_bar     [n_fixed, R, 2] (or [R,2] when reduce_all): d/d(grid point), per fixed point
+ *   objects_bar  [n_objects,2,2]   phis_bar [n_objects]   fixed_bar [n_fixed,2]   alpha_bar [1]
+ * Scene-parameter cotangents are reduced over the whole grid with fp32 atomics (order not fixed).
+ */
+int d2d_power_bwd(const D2DProblem *p, const float *Zbar, float *Z_out, float *grid_bar,
+                  float *objects_bar, float *phis_bar, float *fixed_bar, float *alpha_bar,
+                  void *stream);
+
+/*
+ * Host-buffer convenience entry used for end-to-end timing and by callers without device arrays:
+ * every pointer of `p` and every output is a HOST pointer; the call stages inputs to the device,
+ * runs forward (and backward when any *_bar / want_grad output is non-NULL), copies results back
+ * and synchronises `stream` before returning.  `device` is the CUDA ordinal.
+ */
+int d2d_power_host(const D2DProblem *p, const float *Zbar, float *Z, float *grid_bar,
+                   float *objects_bar, float *phis_bar, float *fixed_bar, float *alpha_bar,
+                   int32_t device);
+
+/* Kernel launches issued by this library since load (for the bench's gpu_launches claim). */
+int64_t d2d_launch_count(void);
+
+/* FP32 FMA-chain microbenchmark used as the roofline denominator: runs `iters` dependent-free
+ * FMA rounds on every SM and writes the executed flop count to *flops (host).  Asynchronous. */
+int d2d_fma_peak_launch(float *sink /*device, >= 1 float*/, int32_t iters, double *flops /*host*/,
+                        void *stream);
+
+const char *d2d_last_error(void);
+int32_t d2d_abi_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DIFFERT2D_B200_H_ */

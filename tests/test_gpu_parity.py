@@ -1,0 +1,207 @@
+"""
+GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle on the same inputs.
+
+Bars (BASELINE.json north_star): candidate lists and hard-logic validity masks bit-exact;
+power maps rtol 1e-5; gradients rtol 1e-4 (fp32).  Tolerances are written where they are used.
+"""
+import numpy as np
+import pytest
+import torch
+
+import differt2d_b200 as d
+from differt2d_b200 import functional as F
+from oracle import c_oracle as CO
+from oracle import ref_torch as R
+from tests import helpers as H
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["hard", "hard_sigmoid", "sigmoid"]
+
+
+def scenes():
+    out = {
+        "square": d.Scene.square_scene(),
+        "obstacle": d.Scene.square_scene_with_obstacle(),
+        "wall": d.Scene.square_scene_with_wall(),
+        "basic": d.Scene.basic_scene(),
+        "geojson": d.Scene.from_geojson(H.geojson_text()),
+    }
+    out["geojson_norm"] = H.normalised(out["geojson"])
+    return out
+
+
+SCENES = scenes()
+
+
+def _grid(scene, n, m, kind):
+    if kind == "bbox":  # the reference's own grid: includes points ON the walls
+        X, Y = scene.grid(m, n)
+    else:
+        X, Y = H.jittered_grid(scene, n, m, seed=3)
+    return np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+
+
+def _cfg(mode, **kw):
+    return F.TraceConfig(mode=mode, **kw)
+
+
+@pytest.mark.parametrize("n,k,f", [(8, 0, ()), (8, 1, ()), (8, 2, ()), (28, 2, ()), (6, 2, (0, 1, 2, 4, 5)),
+                                    (5, 3, (2,)), (7, 4, ()), (500, 2, ()), (40, 3, (3, 9))])
+def test_candidates_device_bit_exact(n, k, f):
+    """scene.py:122-175 — integer decode kernel vs the oracle's depth-first enumeration."""
+    got = F.candidates(n, k, f, device="cuda")
+    want = CO.candidates(n, k, list(f))
+    assert got.dtype == np.int32 and got.shape == want.shape
+    assert np.array_equal(got, want)
+    assert np.array_equal(F.candidates(n, k, f), want)  # host odometer of the same library
+
+
+@pytest.mark.parametrize("name", ["square", "obstacle", "wall", "basic", "geojson", "geojson_norm"])
+@pytest.mark.parametrize("grid_kind", ["bbox", "jitter"])
+def test_hard_masks_and_map_bit_exact(name, grid_kind):
+    """Hard logic: validity of every (receiver, candidate) and the accumulated map, bit for bit."""
+    sc = SCENES[name]
+    X, Y = _grid(sc, 48, 40, grid_kind)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    Zo, vo = CO.power_map(xys, fixed, grid, max_order=2, mode="hard", want_valid=True)
+    Z, v = F.power_fwd(_cfg("hard", max_order=2), xys, fixed, grid, want_valid=True, device="cuda")
+    v = v.cpu().numpy()
+    assert np.array_equal(v, vo), f"{int((v != vo).sum())} of {v.size} hard validity flags differ"
+    assert np.array_equal(Z.cpu().numpy(), Zo)
+
+
+@pytest.mark.parametrize("name", ["obstacle", "basic", "geojson", "geojson_norm"])
+@pytest.mark.parametrize("mode", ["hard_sigmoid", "sigmoid"])
+@pytest.mark.parametrize("alpha", [1.0, 10.0, 100.0, 1000.0])
+def test_smooth_validity_and_map(name, mode, alpha):
+    sc = SCENES[name]
+    X, Y = _grid(sc, 32, 36, "bbox")
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    Zo, vo = CO.power_map(xys, fixed, grid, max_order=2, mode=mode, alpha=alpha, want_valid=True)
+    Z, v = F.power_fwd(_cfg(mode, max_order=2), xys, fixed, grid, alpha=alpha, want_valid=True, device="cuda")
+    v = v.cpu().numpy()
+    if mode == "hard_sigmoid":
+        # same monotone map applied to bit-identical pre-activations: bit-exact
+        assert np.array_equal(v, vo)
+        np.testing.assert_allclose(Z.cpu().numpy(), Zo, rtol=1e-6, atol=0)
+    else:
+        # expf (device) vs expf (glibc): a few ulp on the activation
+        np.testing.assert_allclose(v, vo, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(Z.cpu().numpy(), Zo, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("role", ["receivers", "transmitters"])
+@pytest.mark.parametrize("reduce_all", [False, True])
+def test_multi_fixed_and_roles(role, reduce_all):
+    sc = d.Scene.basic_scene().update_transmitters(tx2=d.Point(xy=[0.7, 0.6])).update_receivers(
+        rx2=d.Point(xy=[0.8, 0.3]), rx3=d.Point(xy=[0.15, 0.75]))
+    X, Y = _grid(sc, 24, 28, "jitter")
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, _, _ = sc.packed_objects()
+    src = sc.transmitters if role == "receivers" else sc.receivers
+    fixed = np.stack([p.xy for p in src.values()])
+    Zo = CO.power_map(xys, fixed, grid, grid_role=role, max_order=2, mode="hard", reduce_all=reduce_all)
+    Z = F.power_fwd(_cfg("hard", max_order=2, grid_role=role, reduce_all=reduce_all), xys, fixed, grid, device="cuda")
+    assert np.array_equal(Z.cpu().numpy(), Zo)
+
+
+def _oracle_vjp(sc, X, Y, Zbar, mode, alpha, role="receivers", max_order=2):
+    osc = H.oracle_scene_from_product(sc)
+    with R.clean_gradients():
+        return R.power_map_and_vjp(osc, X, Y, Zbar, grid_role=role, max_order=max_order, approx=mode != "hard",
+                                   alpha=alpha, function="sigmoid" if mode == "sigmoid" else "hard_sigmoid")
+
+
+def _close(got, want, rtol, what):
+    got = np.asarray(got, np.float64)
+    want = np.asarray(want, np.float64)
+    scale = max(np.abs(want).max(), 1e-30)
+    err = np.abs(got - want).max() / scale
+    assert err <= rtol, f"{what}: max |diff| / max |want| = {err:.3e} > {rtol:g}"
+
+
+@pytest.mark.parametrize("name", ["obstacle", "basic", "geojson_norm"])
+@pytest.mark.parametrize("mode,alpha", [("hard", 100.0), ("hard_sigmoid", 20.0), ("hard_sigmoid", 100.0),
+                                        ("sigmoid", 10.0), ("sigmoid", 100.0)])
+def test_vjp_against_autograd_oracle(name, mode, alpha):
+    """Reverse mode w.r.t. grid points, object vertices, TX and alpha vs torch autograd of the oracle."""
+    sc = SCENES[name]
+    n, m = (12, 14) if name == "geojson_norm" else (20, 22)
+    X, Y = _grid(sc, n, m, "jitter")
+    rng = np.random.default_rng(7)
+    Zbar = rng.standard_normal(X.shape).astype(np.float32)
+    Zo, go = _oracle_vjp(sc, X, Y, Zbar, mode, alpha)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    out = F.power_bwd(_cfg(mode, max_order=2, reduce_all=True), xys, fixed, grid, Zbar.reshape(-1), alpha=alpha,
+                      device="cuda")
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
+    _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar")
+    _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar")
+    _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar")
+    if mode != "hard":
+        _close(out["alpha"], go["alpha"].numpy().reshape(1), 1e-4, "alpha_bar")
+    else:
+        assert out["alpha"][0] == 0.0
+
+
+def test_scene_api_matches_reference_los_kats():
+    """tests/test_scene.py:487-627 of the reference: LOS maps are X^2+Y^2, grads [2X, 2Y], shapes/dtypes/order."""
+    sc = d.Scene(transmitters={"tx0": d.Point(xy=[0.0, 0.0]), "tx1": d.Point(xy=[0.0, 0.0])},
+                 receivers={"rx": d.Point(xy=[0.0, 0.0])}, objects=[])
+    x = np.linspace(-2, 2, 30, dtype=np.float32)
+    y = np.linspace(-1, 3, 20, dtype=np.float32)
+    X, Y = np.meshgrid(x, y)
+    res = list(sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=d.length_squared, max_order=1, approx=False))
+    assert [k for k, _ in res] == ["tx0", "tx1"]
+    for _, Z in res:
+        assert Z.shape == X.shape and Z.dtype == np.float32
+        np.testing.assert_allclose(Z, X * X + Y * Y, rtol=1e-5, atol=1e-6)
+    Z = sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=d.length_squared, reduce_all=True, approx=False)
+    np.testing.assert_allclose(Z, 2 * (X * X + Y * Y), rtol=1e-5, atol=1e-6)
+    for _, dZ in sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=d.length_squared, grad=True, approx=False):
+        assert dZ.shape == (*X.shape, 2)
+        np.testing.assert_allclose(dZ, np.stack([2 * X, 2 * Y], -1), rtol=1e-4, atol=1e-5)
+    for _, (Z, dZ) in sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=d.length_squared, value_and_grad=True,
+                                                                  approx=False):
+        np.testing.assert_allclose(Z, X * X + Y * Y, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(dZ, np.stack([2 * X, 2 * Y], -1), rtol=1e-4, atol=1e-5)
+    res = list(sc.accumulate_on_transmitters_grid_over_paths(X, Y, fun=d.length_squared, approx=False))
+    assert [k for k, _ in res] == ["rx"]
+    np.testing.assert_allclose(res[0][1], X * X + Y * Y, rtol=1e-5, atol=1e-6)
+
+
+def test_accumulate_over_paths_kat():
+    """tests/test_scene.py:443-485 of the reference: 2, 1, 1, 2 and reduce_all -> 6."""
+    sc = d.Scene(transmitters={"tx0": d.Point(xy=[0.0, 0.0]), "tx1": d.Point(xy=[1.0, 0.0])},
+                 receivers={"rx0": d.Point(xy=[1.0, 1.0]), "rx1": d.Point(xy=[0.0, 1.0])}, objects=[])
+    got = list(sc.accumulate_over_paths(fun=d.length_squared, max_order=1, approx=False))
+    assert [(a, b) for a, b, _ in got] == [("tx0", "rx0"), ("tx0", "rx1"), ("tx1", "rx0"), ("tx1", "rx1")]
+    np.testing.assert_allclose([v for _, _, v in got], [2.0, 1.0, 1.0, 2.0], rtol=1e-6)
+    tot = sc.accumulate_over_paths(fun=d.length_squared, reduce_all=True, max_order=1, approx=False)
+    np.testing.assert_allclose(tot, 6.0, rtol=1e-6)
+
+
+def test_autograd_function_matches_direct_vjp():
+    sc = SCENES["obstacle"]
+    X, Y = _grid(sc, 16, 16, "jitter")
+    xys, _, _ = sc.packed_objects()
+    dev = torch.device("cuda")
+    xy_t = torch.tensor(xys, device=dev, requires_grad=True)
+    fixed = torch.tensor([[0.2, 0.2]], device=dev, requires_grad=True)
+    grid = torch.tensor(np.stack([X, Y], -1).reshape(-1, 2), device=dev, requires_grad=True)
+    alpha = torch.tensor(50.0, device=dev, requires_grad=True)
+    cfg = _cfg("hard_sigmoid", max_order=2, reduce_all=True)
+    Z = F.power_map(xy_t, fixed, grid, cfg=cfg, alpha=alpha)
+    Z.sum().backward()
+    ref = F.power_bwd(cfg, xys, fixed.detach(), grid.detach(), None, alpha=50.0, device=dev)
+    assert torch.allclose(xy_t.grad, ref["objects"], rtol=1e-3, atol=1e-3 * ref["objects"].abs().max().item())
+    assert torch.allclose(grid.grad, ref["grid"].reshape(-1, 2), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(alpha.grad.reshape(1), ref["alpha"], rtol=1e-3)
