@@ -52,8 +52,8 @@ class D2DProblem(C.Structure):
         ("tol", C.c_float),
         ("patch", C.c_float),
         ("fun", C.c_int32),
-        ("r_coef", C.c_float),
-        ("height", C.c_float),
+        ("r_coef", C.c_double),
+        ("height", C.c_double),
         ("reduce_all", C.c_int32),
         ("grad_mode", C.c_int32),
     ]

@@ -148,8 +148,8 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
     k.patch = p->patch;
     k.lr = p->lr;
     // utils.py:52-54 — Python folds r_coef**n and height*height in double, JAX then casts to f32
-    k.h2 = (float)((double)p->height * (double)p->height);
-    for (int i = 0; i <= d2d::kMaxOrder; ++i) k.rc_pow[i] = (float)std::pow((double)p->r_coef, (double)i);
+    k.h2 = (float)(p->height * p->height);
+    for (int i = 0; i <= d2d::kMaxOrder; ++i) k.rc_pow[i] = (float)std::pow(p->r_coef, (double)i);
     const int m = build_blocked(p->n_objects, p->filter_nodes, p->n_filter, k.blocked);
     if (m < 0) return fail(D2D_ERR_INVALID_ARGUMENT, "bad filter_nodes");
     long long total = 0;
@@ -180,8 +180,8 @@ void d2d_problem_defaults(D2DProblem* p) {
     p->tol = 1e-2f;     // geometry.py:915
     p->patch = 0.0f;    // defaults.py:7
     p->fun = D2D_FUN_RECEIVED_POWER;
-    p->r_coef = 0.5f;  // defaults.py:12
-    p->height = 0.1f;  // defaults.py:15
+    p->r_coef = 0.5;  // defaults.py:12
+    p->height = 0.1;  // defaults.py:15
     p->grad_mode = D2D_GRAD_CLEAN;
 }
 

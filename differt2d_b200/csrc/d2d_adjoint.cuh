@@ -11,7 +11,9 @@
 
 namespace d2d {
 
-__device__ __forceinline__ float dot2(const float2 a, const float2 b) { return fmaf(a.x, b.x, a.y * b.y); }
+// plain (uncontracted) on purpose: the loss cotangent is proportional to the residual vector e, which is
+// pure rounding noise for specular paths; recomputing it canonically keeps it equal to the forward's.
+__device__ __forceinline__ float dot2(const float2 a, const float2 b) { return a.x * b.x + a.y * b.y; }
 
 // v_hat = v / len with len = |v| (1 when |v| == 0).  Returns v_bar for a given v_hat_bar.
 __device__ __forceinline__ float2 normalize_adj(const float2 v, const float2 vh_bar) {

@@ -125,13 +125,15 @@ __device__ __forceinline__ float path_vjp_image(const SceneTab& T, const KParams
         const int cnt = (v1 == valid) + (v2 == valid) + (v3 == valid);
         const float share = zbar * val / (float)cnt;  // jnp.min splits evenly among ties
         if (v1 == valid && on_i >= 0) {
-            const float dz = act_dz<MODE>(onx, alpha);
-            const float onx_bar = share * alpha * dz;
-            alpha_bar += share * onx * dz;
-            const float one_minus = 1.0f - on_s;
-            float s_bar = 0.f;
-            if (on_s < one_minus) s_bar = onx_bar;
-            else if (on_s > one_minus) s_bar = -onx_bar;
+            // contains_parametric = minimum(act(s - 0), act(1 - s)) (geometry.py:608-621): the tie rule of
+            // jnp.minimum (1/2, 1/2) applies to the ACTIVATED values, which tie far more often than the
+            // pre-activations do (the activation is not injective in fp32).
+            const float xg = on_s, xl = 1.0f - on_s;
+            const float Ag = act<MODE>(xg, alpha), Al = act<MODE>(xl, alpha);
+            const float wg = Ag < Al ? 1.0f : (Ag == Al ? 0.5f : 0.0f), wl = 1.0f - wg;
+            const float dg = act_dz<MODE>(xg, alpha), dl = act_dz<MODE>(xl, alpha);
+            const float s_bar = share * alpha * (wg * dg - wl * dl);
+            alpha_bar += share * (wg * xg * dg + wl * xl * dl);
             if (s_bar != 0.f) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
@@ -161,10 +163,8 @@ __device__ __forceinline__ float path_vjp_image(const SceneTab& T, const KParams
             }
         }
         if (v2 == valid && jj >= 0 && interx != -CUDART_INF_F) {
-            const float dz = act_dz<MODE>(interx, alpha);
-            const float ix_bar = -share * alpha * dz;
-            alpha_bar += -share * interx * dz;
-            if (ix_bar != 0.f) {
+            const float gsh = -share;  // d valid / d a_in = -1
+            {
                 float2 P = X[0], Q = X[1];
 #pragma unroll
                 for (int i = 0; i <= K; ++i)
@@ -176,12 +176,19 @@ __device__ __forceinline__ float path_vjp_image(const SceneTab& T, const KParams
                 const float b = w.z * Cy - w.w * Cx;
                 const float d = w.w * B.x - w.z * B.y;
                 const float ta = a / d, tb = b / d;
+                // hit = minimum(minimum(ge_a, le_a), minimum(ge_b, le_b)) on ACTIVATED values (geometry.py:167-173)
                 const float x1 = ta + kTolSeg, x2 = kHiSeg - ta, x3 = tb + kTolSeg, x4 = kHiSeg - tb;
-                const float hx = fminf(fminf(x1, x2), fminf(x3, x4));
-                const int ties = (x1 == hx) + (x2 == hx) + (x3 == hx) + (x4 == hx);
-                const float g = ix_bar / (float)ties;
-                const float ta_bar = (x1 == hx ? g : 0.f) - (x2 == hx ? g : 0.f);
-                const float tb_bar = (x3 == hx ? g : 0.f) - (x4 == hx ? g : 0.f);
+                const float A1 = act<MODE>(x1, alpha), A2 = act<MODE>(x2, alpha);
+                const float A3 = act<MODE>(x3, alpha), A4 = act<MODE>(x4, alpha);
+                const float Ta = fminf(A1, A2), Tb = fminf(A3, A4);
+                const float wa = Ta < Tb ? 1.0f : (Ta == Tb ? 0.5f : 0.0f), wb = 1.0f - wa;
+                const float w1 = wa * (A1 < A2 ? 1.0f : (A1 == A2 ? 0.5f : 0.0f)), w2 = wa - w1;
+                const float w3 = wb * (A3 < A4 ? 1.0f : (A3 == A4 ? 0.5f : 0.0f)), w4 = wb - w3;
+                const float d1 = act_dz<MODE>(x1, alpha), d2 = act_dz<MODE>(x2, alpha);
+                const float d3 = act_dz<MODE>(x3, alpha), d4 = act_dz<MODE>(x4, alpha);
+                alpha_bar += gsh * (w1 * x1 * d1 + w2 * x2 * d2 + w3 * x3 * d3 + w4 * x4 * d4);
+                const float ta_bar = gsh * alpha * (w1 * d1 - w2 * d2);
+                const float tb_bar = gsh * alpha * (w3 * d3 - w4 * d4);
                 const float a_bar = ta_bar / d, b_bar = tb_bar / d;
                 const float d_bar = -(ta_bar * ta + tb_bar * tb) / d;
                 float2 Bb, Cb, Ab;

@@ -92,8 +92,8 @@ typedef struct D2DProblem {
     float patch;            /* wall lengthening for the occlusion test (geometry.py:632-635)      */
     /* ---- accumulated function --------------------------------------------------------------- */
     int32_t fun;    /* D2D_FUN_*                                                                  */
-    float r_coef;   /* defaults.py:12                                                             */
-    float height;   /* defaults.py:15                                                             */
+    double r_coef;  /* defaults.py:12 — Python floats: r_coef**k and height*height are folded in    */
+    double height;  /* defaults.py:15   double precision and then cast to f32 (utils.py:52-54)      */
     int32_t reduce_all; /* sum over the fixed points (scene.py:1939-1952)                          */
     int32_t grad_mode;  /* D2D_GRAD_*                                                              */
 } D2DProblem;

@@ -58,3 +58,22 @@ def jittered_grid(scene, n, m, seed=0, margin=0.02):
     y = bb[0, 1] + w[1] * (margin + (1 - 2 * margin) * np.sort(rng.random(n)))
     X, Y = np.meshgrid(x.astype(np.float32), y.astype(np.float32))
     return X, Y
+
+
+def generic_position(scene, seed=11, eps=2e-3):
+    """Moves every object vertex by a small random offset so that no two walls stay collinear or share
+    end-point heights.  Axis-aligned canned scenes contain STRUCTURAL ties (e.g. ta + tb == 1 for a whole
+    region of receivers), where min/max sub-gradients w.r.t. the wall vertices depend on last-bit noise in
+    the reference itself; parity of d/d(vertices) is only meaningful away from those ties."""
+    import differt2d_b200 as d
+
+    rng = np.random.default_rng(seed)
+    objs = []
+    for o in scene.objects:
+        if isinstance(o, d.Vertex):
+            objs.append(d.Vertex(xy=o.xy + rng.uniform(-eps, eps, 2).astype(np.float32)))
+        elif isinstance(o, d.RIS):
+            objs.append(d.RIS(xys=o.xys + rng.uniform(-eps, eps, (2, 2)).astype(np.float32), phi=o.phi))
+        else:
+            objs.append(d.Wall(xys=o.xys + rng.uniform(-eps, eps, (2, 2)).astype(np.float32)))
+    return d.Scene(scene.transmitters, scene.receivers, objs)

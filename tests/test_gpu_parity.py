@@ -91,7 +91,7 @@ def test_smooth_validity_and_map(name, mode, alpha):
         np.testing.assert_allclose(Z.cpu().numpy(), Zo, rtol=1e-6, atol=0)
     else:
         # expf (device) vs expf (glibc): a few ulp on the activation
-        np.testing.assert_allclose(v, vo, rtol=1e-5, atol=1e-7)
+        np.testing.assert_allclose(v, vo, rtol=1e-5, atol=2.5e-7)  # 1 - a_in cancels: 2 ulp at 1.0
         np.testing.assert_allclose(Z.cpu().numpy(), Zo, rtol=1e-5, atol=1e-6)
 
 
@@ -128,9 +128,11 @@ def _close(got, want, rtol, what):
 @pytest.mark.parametrize("name", ["obstacle", "basic", "geojson_norm"])
 @pytest.mark.parametrize("mode,alpha", [("hard", 100.0), ("hard_sigmoid", 20.0), ("hard_sigmoid", 100.0),
                                         ("sigmoid", 10.0), ("sigmoid", 100.0)])
-def test_vjp_against_autograd_oracle(name, mode, alpha):
-    """Reverse mode w.r.t. grid points, object vertices, TX and alpha vs torch autograd of the oracle."""
-    sc = SCENES[name]
+@pytest.mark.parametrize("generic", [False, True])
+def test_vjp_against_autograd_oracle(name, mode, alpha, generic):
+    """Reverse mode w.r.t. grid points, object vertices, TX and alpha vs torch autograd of the oracle.
+    d/d(vertices) is compared on the generic-position variant only (see helpers.generic_position)."""
+    sc = H.generic_position(SCENES[name]) if generic else SCENES[name]
     n, m = (12, 14) if name == "geojson_norm" else (20, 22)
     X, Y = _grid(sc, n, m, "jitter")
     rng = np.random.default_rng(7)
@@ -145,7 +147,8 @@ def test_vjp_against_autograd_oracle(name, mode, alpha):
     np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
     _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar")
     _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar")
-    _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar")
+    if generic or mode == "hard":
+        _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar")
     if mode != "hard":
         _close(out["alpha"], go["alpha"].numpy().reshape(1), 1e-4, "alpha_bar")
     else:
