@@ -1,0 +1,97 @@
+"""
+Multi-GPU plumbing: one process per GPU, the receiver grid sharded by contiguous row blocks
+(SURVEY §8e).  Forward maps and per-receiver cotangents need no communication (disjoint rows);
+the scene-parameter cotangents (object vertices, RIS angles, fixed points, alpha — a few KB) are
+partial sums and take ONE all-reduce per backward call (NCCL over NVLink on GPUs, gloo in CPU tests).
+"""
+
+from __future__ import annotations
+
+import os
+from typing import Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def row_block(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
+    """Contiguous row range [r0, r1) of `rank`; the first n_rows % world ranks get one extra row."""
+    base, extra = divmod(n_rows, world)
+    r0 = rank * base + min(rank, extra)
+    return r0, r0 + base + (1 if rank < extra else 0)
+
+
+def init(world: Optional[int] = None, rank: Optional[int] = None, backend: Optional[str] = None):
+    """Initialises torch.distributed from the torchrun environment (MASTER_ADDR defaults to 127.0.0.1)."""
+    if dist.is_initialized():
+        return dist
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    os.environ.setdefault("MASTER_PORT", "29500")
+    world = int(os.environ.get("WORLD_SIZE", "1")) if world is None else world
+    rank = int(os.environ.get("RANK", "0")) if rank is None else rank
+    if backend is None:
+        backend = "nccl" if torch.cuda.is_available() else "gloo"
+    kw = {}
+    if backend == "nccl":
+        kw["device_id"] = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    dist.init_process_group(backend=backend, world_size=world, rank=rank, **kw)
+    return dist
+
+
+def allreduce_sum_(buf: torch.Tensor) -> torch.Tensor:
+    """In-place sum over ranks of the packed scene-parameter cotangent buffer (on the current stream)."""
+    if dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(buf, op=dist.ReduceOp.SUM)
+    return buf
+
+
+def pack_param_grads(objects_bar, phis_bar, fixed_bar, alpha_bar) -> torch.Tensor:
+    """objects [N,2,2] | phis [N] | fixed [T,2] | alpha [1] -> one flat fp32 buffer (one collective)."""
+    return torch.cat([objects_bar.reshape(-1), phis_bar.reshape(-1), fixed_bar.reshape(-1), alpha_bar.reshape(-1)])
+
+
+def unpack_param_grads(buf: torch.Tensor, n_objects: int, n_fixed: int):
+    o = 0
+    objects = buf[o:o + 4 * n_objects].reshape(n_objects, 2, 2); o += 4 * n_objects
+    phis = buf[o:o + n_objects]; o += n_objects
+    fixed = buf[o:o + 2 * n_fixed].reshape(n_fixed, 2); o += 2 * n_fixed
+    return objects, phis, fixed, buf[o:o + 1]
+
+
+def max_over_ranks(value: float, device) -> float:
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device if dist.get_backend() == "nccl" else "cpu")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier() -> None:
+    if dist.is_initialized():
+        dist.barrier()
+
+
+def shutdown() -> None:
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
+def sharded_power_vjp(cfg, xys, fixed, X, Y, Zbar=None, *, alpha=100.0, kinds=None, phis=None, device=None):
+    """
+    Row-sharded forward + VJP: this rank traces rows row_block(n, world, rank) of the (n, m) grid and
+    returns its slice of Z / grid_bar plus the ALL-REDUCED scene-parameter cotangents.
+    """
+    from . import functional as F
+
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    n = X.shape[0]
+    r0, r1 = row_block(n, world, rank)
+    Xs, Ys = torch.as_tensor(X[r0:r1]), torch.as_tensor(Y[r0:r1])
+    grid = torch.stack((Xs, Ys), dim=-1).reshape(-1, 2)
+    zb = None if Zbar is None else torch.as_tensor(Zbar[r0:r1]).reshape(-1)
+    out = F.power_bwd(cfg, xys, fixed, grid, zb, kinds=kinds, phis=phis, alpha=alpha, device=device)
+    n_obj = out["objects"].shape[0]
+    buf = pack_param_grads(out["objects"], out["phis"], out["fixed"], out["alpha"])
+    allreduce_sum_(buf)
+    out["objects"], out["phis"], out["fixed"], out["alpha"] = unpack_param_grads(buf, n_obj, out["fixed"].shape[0])
+    out["rows"] = (r0, r1)
+    return out

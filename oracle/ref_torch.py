@@ -713,7 +713,7 @@ def power_map_and_vjp(
     scene: OScene, X, Y, Zbar=None, *, grid_role="receivers", fun="received_power", fun_kwargs=None,
     method="image", min_order=0, max_order=1, filter_nodes=None, x0=None, steps=100, lr=0.1,
     approx=True, alpha=DEFAULT_ALPHA, function="hard_sigmoid", patch=DEFAULT_PATCH, tol=1e-2,
-    wrt=("grid", "xys", "phis", "fixed", "alpha"),
+    wrt=("grid", "xys", "phis", "fixed", "alpha"), cand_stride=1,
 ):
     """
     What ``jax.vjp(lambda scene, tx, grid, alpha: accumulate_…(reduce_all=True, alpha=alpha))``
@@ -734,6 +734,9 @@ def power_map_and_vjp(
     s2 = OScene(xys, scene.kinds, phis)
     logic = Logic(approx, alpha_t, function)
     cands = all_path_candidates(scene.n, min_order, max_order, filter_nodes=filter_nodes)
+    if cand_stride > 1:  # bounded CPU-baseline samples only: every cand_stride-th candidate
+        cands = cands[::cand_stride]
+        x0 = None if x0 is None else x0[::cand_stride]
     Z = torch.zeros((), dtype=F32)
     for t in range(fixed.shape[0]):
         if grid_role == "receivers":
