@@ -24,7 +24,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // Reverse sweep of one ImagePath.  Returns valid * fun; when the path carries gradient, `has` is set
 // and tx_bar / rx_bar / alpha_bar / oa[] / occ_* are filled (not accumulated).
 template <int MODE, int K>
-__device__ __forceinline__ float path_vjp_image(const SceneTab& T, const KParams& p, const float alpha,
+__device__ __noinline__ float path_vjp_image(const SceneTab& T, const KParams& p, const float alpha,
                                                 const Cand<K>& cd, const float2 tx, const float2 rx,
                                                 const float zbar, bool& has, float2& tx_bar, float2& rx_bar,
                                                 float& alpha_bar, ObjAdj (&oa)[K > 0 ? K : 1], int& occ_j,
@@ -292,8 +292,15 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
         int occ_j = -1;
         float4 occ_bar = make_float4(0.f, 0.f, 0.f, 0.f);
         if (active) {
-            const float c = path_vjp_image<MODE, K>(T, p, alpha, cd, tx, rx, zbar, has, txb, rxb, ab, oa, occ_j, occ_bar);
-            A.acc = A.acc + c;
+            // light re-trace first (same code as the forward kernel); the reverse sweep is out of line and
+            // only runs for the few paths whose validity is non-zero
+            float2 X[K + 2];
+            image_path<K>(T, cd, tx, rx, X);
+            const float valid = validity<MODE, K, true>(T, p, alpha, cd, X, 0.0f);
+            if (valid != 0.0f) {
+                const float c = path_vjp_image<MODE, K>(T, p, alpha, cd, tx, rx, zbar, has, txb, rxb, ab, oa, occ_j, occ_bar);
+                A.acc = A.acc + c;
+            }
         }
         if (has) {
             const float2 gb = TXGRID ? txb : rxb;

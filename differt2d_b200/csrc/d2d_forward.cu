@@ -25,7 +25,7 @@ __device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, c
         float2 X[K + 2];
         float loss;
         construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-        const float valid = validity<MODE, K>(T, p, alpha, cd, X, loss);
+        const float valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
         if (valid != 0.0f) {
             float r;
             acc = acc + valid * path_value<K>(p, X, r);  // scene.py:1909

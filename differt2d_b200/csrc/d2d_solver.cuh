@@ -60,9 +60,11 @@ template <int METHOD, int K>
 __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams& p, const Cand<K>& cd,
                                                const float2 tx, const float2 rx, const long long col,
                                                float2 (&X)[K + 2], float& loss) {
+    // `loss` is only produced here for MinPath (the solver's own value, optimize.py:96-97); for the
+    // other methods it is path_loss(X), evaluated lazily by validity<.., LAZY_LOSS = true>.
+    loss = 0.0f;
     if (METHOD == D2D_METHOD_IMAGE || K == 0) {
         image_path<K>(T, cd, tx, rx, X);
-        loss = path_loss<K>(T, cd, X);
         return;
     }
     constexpr int KK = K > 0 ? K : 1;
@@ -104,8 +106,9 @@ __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams&
         }
     }
     place_points<K>(T, cd, th, X);
-    if (METHOD == D2D_METHOD_FERMAT) loss = path_loss<K>(T, cd, X);  // geometry.py:1202-1204
-    else {
+    if (METHOD == D2D_METHOD_FERMAT) {
+        // geometry.py:1202-1204: loss = path_loss(xys), left to validity()
+    } else {
         if (p.steps <= 0) {
             float2 G[K + 2];
             last = solver_loss_grad<METHOD, K>(T, cd, X, G);

@@ -124,11 +124,13 @@ __device__ __forceinline__ float path_value(const KParams& p, const float2 (&X)[
     return r * r;
 }
 
-// Path.is_valid (geometry.py:908-963) for an already constructed path, then valid * fun.
-// Returns the validity (0/1 in hard mode); `contrib` = valid * fun (0 when the path is dead).
-template <int MODE, int K>
+// Path.is_valid (geometry.py:908-963) for an already constructed path.
+// Returns the validity (0/1 in hard mode).  The three conjuncts commute, so the cheap ones run first and
+// the path loss (two normalisations per interaction) is only evaluated for paths that lie on their objects:
+// LAZY_LOSS = true computes it here from X (Image / Fermat), false takes the solver's value (MinPath).
+template <int MODE, int K, bool LAZY_LOSS>
 __device__ __forceinline__ float validity(const SceneTab& T, const KParams& p, const float alpha,
-                                          const Cand<K>& cd, const float2 (&X)[K + 2], const float loss) {
+                                          const Cand<K>& cd, const float2 (&X)[K + 2], float loss) {
     // 1. on_objects
     const float onx = on_objects_x<K>(T, cd, X);
     float a_on = 1.0f;
@@ -139,6 +141,7 @@ __device__ __forceinline__ float validity(const SceneTab& T, const KParams& p, c
         if (a_on == 0.0f) return 0.0f;
     }
     // 2. loss below tolerance
+    if (LAZY_LOSS) loss = path_loss<K>(T, cd, X);
     const float lx = p.tol - loss;
     float a_l = 1.0f;
     if (MODE == D2D_MODE_HARD) {
