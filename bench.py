@@ -213,7 +213,7 @@ def cpu_baseline_sample(sc, args) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--coords", default="raw", choices=["raw", "normalised"])
@@ -247,7 +247,7 @@ def main() -> None:
     r0, r1 = D.row_block(n_rows, world, rank)
     grid_h = np.stack([X[r0:r1], Y[r0:r1]], -1).reshape(-1, 2).astype(np.float32)
     R = grid_h.shape[0]
-    cfg = F.TraceConfig(mode=MODE, max_order=MAX_ORDER, reduce_all=True)
+    cfg = F.TraceConfig(mode=MODE, max_order=MAX_ORDER, reduce_all=True, grid_cols=n_cols)
     n_obj = xys.shape[0]
     n_cand = sum(1 if k == 0 else n_obj * (n_obj - 1) ** (k - 1) for k in range(MAX_ORDER + 1))
     T = fixed.shape[0]
@@ -338,6 +338,7 @@ def main() -> None:
     hp.n_fixed, hp.fixed_xy = T, fixed.ctypes.data
     hp.n_grid, hp.grid_xy = R, grid_p.data_ptr()
     hp.max_order, hp.mode, hp.alpha, hp.reduce_all = MAX_ORDER, L.MODE_HARD_SIGMOID, ALPHA, 1
+    hp.grid_cols = n_cols
 
     def e2e_step():
         L.check(lib.d2d_power_host(C.byref(hp), zbar_p.data_ptr(), Z_p.data_ptr(), gbar_p.data_ptr(),

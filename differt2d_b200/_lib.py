@@ -38,6 +38,7 @@ class D2DProblem(C.Structure):
         ("n_grid", C.c_int64),
         ("grid_xy", C.c_void_p),
         ("grid_role", C.c_int32),
+        ("grid_cols", C.c_int32),
         ("min_order", C.c_int32),
         ("max_order", C.c_int32),
         ("filter_nodes", C.c_void_p),
@@ -56,6 +57,7 @@ class D2DProblem(C.Structure):
         ("height", C.c_double),
         ("reduce_all", C.c_int32),
         ("grad_mode", C.c_int32),
+        ("no_cull", C.c_int32),
     ]
 
 

@@ -10,6 +10,7 @@
 // Per-grid-point cotangents are written directly (disjoint).  Scene-parameter cotangents are
 // reduced warp (shuffle) -> CTA (shared-memory atomics) -> device (global fp32 atomics); the
 // multi-GPU all-reduce of these few KB happens in the host layer (differt2d_b200/distributed.py).
+#include "d2d_driver.cuh"
 #include "d2d_launch.h"
 #include "d2d_solver.cuh"
 
@@ -275,76 +276,75 @@ struct BwdAcc {
 };
 
 template <int MODE, int K, bool TXGRID>
-__device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& p, const float alpha,
-                                              const float2 tx, const float2 rx, const bool active, const float zbar,
-                                              BwdAcc& A, float* s_obj, float* s_phi) {
-    Odometer<K> od;
-    if (!od.first(T.n_allowed)) return;
+__device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
+                                              const float alpha, const float2 fx, const float2 g, const long long col0,
+                                              int& buf, const float zbar, BwdAcc& A, float* s_obj, float* s_phi) {
     constexpr int KK = K > 0 ? K : 1;
-    do {
-        Cand<K> cd;
-#pragma unroll
-        for (int i = 0; i < K; ++i) cd.c[i] = T.allowed[od.pos[i]];
-        bool has = false;
-        float2 txb = make_float2(0.f, 0.f), rxb = make_float2(0.f, 0.f);
-        float ab = 0.f;
-        ObjAdj oa[KK];
-        int occ_j = -1;
-        float4 occ_bar = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (active) {
-            // light re-trace first (same code as the forward kernel); the reverse sweep is out of line and
-            // only runs for the few paths whose validity is non-zero
-            float2 X[K + 2];
-            image_path<K>(T, cd, tx, rx, X);
-            const float valid = validity<MODE, K, true>(T, p, alpha, cd, X, 0.0f);
-            if (valid != 0.0f) {
-                const float c = path_vjp_image<MODE, K>(T, p, alpha, cd, tx, rx, zbar, has, txb, rxb, ab, oa, occ_j, occ_bar);
-                A.acc = A.acc + c;
-            }
-        }
-        if (has) {
-            const float2 gb = TXGRID ? txb : rxb;
-            const float2 fb = TXGRID ? rxb : txb;
-            A.grid_bar.x += gb.x; A.grid_bar.y += gb.y;
-            A.fixed_bar.x += fb.x; A.fixed_bar.y += fb.y;
-            A.alpha_bar += ab;
-            if (occ_j >= 0 && s_obj) {
-                atomicAdd(&s_obj[4 * occ_j + 0], occ_bar.x);
-                atomicAdd(&s_obj[4 * occ_j + 1], occ_bar.y);
-                atomicAdd(&s_obj[4 * occ_j + 2], occ_bar.z);
-                atomicAdd(&s_obj[4 * occ_j + 3], occ_bar.w);
-            }
-        }
-        if (K > 0 && s_obj && __any_sync(0xffffffffu, has)) {
-            // every lane holds the same candidate: reduce the interacting objects' cotangents in the warp
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                float ph = 0.f;
-                if (has) {
-                    v = oa[i].to_vertices(T.w0[cd.c[i]], T.w1[cd.c[i]]);
-                    ph = oa[i].phi;
-                }
-                v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-                const bool ris = T.kind[cd.c[i]] == D2D_KIND_RIS;
-                if (ris) ph = warp_sum(ph);
-                if ((threadIdx.x & 31) == 0) {
-                    atomicAdd(&s_obj[4 * cd.c[i] + 0], v.x);
-                    atomicAdd(&s_obj[4 * cd.c[i] + 1], v.y);
-                    atomicAdd(&s_obj[4 * cd.c[i] + 2], v.z);
-                    atomicAdd(&s_obj[4 * cd.c[i] + 3], v.w);
-                    if (ris) atomicAdd(&s_phi[cd.c[i]], ph);
+    const float2 tx = TXGRID ? g : fx;
+    const float2 rx = TXGRID ? fx : g;
+    for_each_candidate<MODE, D2D_METHOD_IMAGE, K, TXGRID>(
+        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long) {
+            bool has = false;
+            float2 txb = make_float2(0.f, 0.f), rxb = make_float2(0.f, 0.f);
+            float ab = 0.f;
+            ObjAdj oa[KK];
+            int occ_j = -1;
+            float4 occ_bar = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (tile.active) {
+                // light re-trace first (same code as the forward kernel); the reverse sweep is out of line
+                // and only runs for the few paths whose validity is non-zero
+                float2 X[K + 2];
+                image_path<K>(T, cd, tx, rx, X);
+                const float valid = validity<MODE, K, true>(T, p, alpha, cd, X, 0.0f);
+                if (valid != 0.0f) {
+                    const float c = path_vjp_image<MODE, K>(T, p, alpha, cd, tx, rx, zbar, has, txb, rxb, ab, oa,
+                                                            occ_j, occ_bar);
+                    A.acc = A.acc + c;
                 }
             }
-        }
-    } while (od.next(T.n_allowed));
+            if (has) {
+                const float2 gb = TXGRID ? txb : rxb;
+                const float2 fb = TXGRID ? rxb : txb;
+                A.grid_bar.x += gb.x; A.grid_bar.y += gb.y;
+                A.fixed_bar.x += fb.x; A.fixed_bar.y += fb.y;
+                A.alpha_bar += ab;
+                if (occ_j >= 0 && s_obj) {
+                    atomicAdd(&s_obj[4 * occ_j + 0], occ_bar.x);
+                    atomicAdd(&s_obj[4 * occ_j + 1], occ_bar.y);
+                    atomicAdd(&s_obj[4 * occ_j + 2], occ_bar.z);
+                    atomicAdd(&s_obj[4 * occ_j + 3], occ_bar.w);
+                }
+            }
+            if (K > 0 && s_obj && __any_sync(0xffffffffu, has)) {
+                // every lane holds the same candidate: reduce the interacting objects' cotangents in the warp
+#pragma unroll
+                for (int i = 0; i < K; ++i) {
+                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                    float ph = 0.f;
+                    if (has) {
+                        v = oa[i].to_vertices(T.w0[cd.c[i]], T.w1[cd.c[i]]);
+                        ph = oa[i].phi;
+                    }
+                    v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+                    const bool ris = T.kind[cd.c[i]] == D2D_KIND_RIS;
+                    if (ris) ph = warp_sum(ph);
+                    if ((threadIdx.x & 31) == 0) {
+                        atomicAdd(&s_obj[4 * cd.c[i] + 0], v.x);
+                        atomicAdd(&s_obj[4 * cd.c[i] + 1], v.y);
+                        atomicAdd(&s_obj[4 * cd.c[i] + 2], v.z);
+                        atomicAdd(&s_obj[4 * cd.c[i] + 3], v.w);
+                        if (ris) atomicAdd(&s_phi[cd.c[i]], ph);
+                    }
+                }
+            }
+        });
 }
 
 template <int MODE, bool TXGRID>
-__global__ void __launch_bounds__(128) power_bwd_kernel(const KParams p, const float* __restrict__ Zbar,
-                                                        const BwdOut out) {
+__global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, const float* __restrict__ Zbar,
+                                                           const BwdOut out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_count;
+    __shared__ DriverShared sh;
     __shared__ float s_red[4][4];
     SceneTab T = carve_tab(smem, p.N);
     const bool want_obj = out.objects_bar != nullptr || out.phis_bar != nullptr;
@@ -355,34 +355,36 @@ __global__ void __launch_bounds__(128) power_bwd_kernel(const KParams p, const f
         s_phi = s_obj + 4 * p.N;
         for (int j = threadIdx.x; j < 5 * p.N; j += blockDim.x) s_obj[j] = 0.f;
     }
-    build_tab(T, p, &s_count);
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    const bool active = r < p.R;
+    build_tab(T, p, &sh.count);
+    const Tile tile = make_tile(p, T, sh);
+    const long long r = tile.r;
+    const bool active = tile.active;
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
     const float2 g = active ? reinterpret_cast<const float2*>(p.grid)[r] : make_float2(0.f, 0.f);
     float zsum = 0.0f;
     float2 gsum = make_float2(0.f, 0.f);
     float alpha_total = 0.f;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int buf = 0;
     for (int t = 0; t < p.T; ++t) {
         const float2 fx = reinterpret_cast<const float2*>(p.fixed)[t];
-        const float2 tx = TXGRID ? g : fx;
-        const float2 rx = TXGRID ? fx : g;
         float zbar = 0.f;
         if (active) zbar = Zbar ? Zbar[p.reduce_all ? r : (long long)t * p.R + r] : 1.0f;
         BwdAcc A;
         A.grid_bar = A.fixed_bar = make_float2(0.f, 0.f);
         A.alpha_bar = 0.f;
         A.acc = 0.f;
+        long long col0 = 0;
         for (int k = p.min_order; k <= p.max_order; ++k) {
             switch (k) {
-                case 0: run_order_bwd<MODE, 0, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
-                case 1: run_order_bwd<MODE, 1, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
-                case 2: run_order_bwd<MODE, 2, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
-                case 3: run_order_bwd<MODE, 3, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
-                case 4: run_order_bwd<MODE, 4, TXGRID>(T, p, alpha, tx, rx, active, zbar, A, s_obj, s_phi); break;
+                case 0: run_order_bwd<MODE, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 1: run_order_bwd<MODE, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 2: run_order_bwd<MODE, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 3: run_order_bwd<MODE, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 4: run_order_bwd<MODE, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
                 default: break;
             }
+            col0 += order_count(k, T.n_allowed);
         }
         if (active) {
             if (p.reduce_all) {
@@ -433,8 +435,8 @@ __global__ void __launch_bounds__(128) power_bwd_kernel(const KParams p, const f
 
 template <int MODE, bool TXGRID>
 static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out, cudaStream_t stream) {
-    const int block = 128;
-    const long long nblk = (p.R + block - 1) / block;
+    const int block = kBlock;
+    const long long nblk = num_tile_blocks(p);
     size_t smem = ((scene_tab_bytes(p.N) + 15) / 16) * 16;
     if (out.objects_bar || out.phis_bar) smem += (size_t)5 * p.N * sizeof(float);
     auto kern = power_bwd_kernel<MODE, TXGRID>;

@@ -45,6 +45,8 @@ struct KParams {
     const float* x0;       // [C,max_order] or nullptr
     const float* alpha_dev;
     long long R;
+    int grid_cols;         // row length of the grid when it is a row-major n x m mesh (0: unknown)
+    int cull;              // tile-level candidate culling on/off (results are identical either way)
     int N, T;
     int min_order, max_order;
     int steps;
@@ -158,7 +160,8 @@ template <int MODE>
 __device__ __forceinline__ float x_zero(float alpha) {
     if (MODE == D2D_MODE_HARD) return 0.0f;  // only hx >= 0 matters (with margin from filter_threshold)
     if (MODE == D2D_MODE_HARD_SIGMOID) return -3.0f / alpha - fabsf(4.0f / alpha) * 1e-5f;
-    return -CUDART_INF_F;  // sigmoid never reaches 0 in a useful range: every test may matter
+    // sigmoid: 1/(1+expf(-z)) is exactly 0 once expf(-z) overflows (-z > 88.73): z <= -89 is safely there
+    return -89.5f / alpha;
 }
 
 // ---- geometry -------------------------------------------------------------------------------

@@ -1,86 +1,94 @@
 // differt2d_b200 — forward power-map kernel.
 //
-// Mapping: one thread per grid point; the CTA walks the candidate list in list order (orders
-// ascending, lexicographic inside an order — scene.py:166-175) so that the per-point accumulation
-// order is the reference's (scene.py:1893-1918).  Every lane of a warp works on the same candidate
-// at the same time: object-table reads are shared-memory broadcasts and the candidate odometer
-// lives in uniform registers.  Nothing but the grid point (8 B) is read from and the map value
-// (4 B) written to HBM per thread; the kernel is FP32-issue bound (DESIGN.md "Roofline").
+// Mapping: one thread per grid point, one CTA per compact tile of 128 points (d2d_driver.cuh).  The
+// CTA walks the candidate list in list order (orders ascending, lexicographic inside an order —
+// scene.py:166-175), so the per-point accumulation order is the reference's (scene.py:1893-1918).
+// Every lane works on the same candidate at the same time: object-table reads are shared-memory
+// broadcasts.  HBM traffic is the grid point (8 B) in and the map value (4 B) out per thread; the
+// kernel is FP32-issue bound (DESIGN.md "Roofline").
+#include "d2d_driver.cuh"
 #include "d2d_launch.h"
-#include "d2d_trace.cuh"
 #include "d2d_solver.cuh"
 
 namespace d2d {
 
-template <int MODE, int METHOD, int K>
-__device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, const float alpha,
-                                          const float2 tx, const float2 rx, float& acc, float* vrow,
-                                          long long& col) {
-    Odometer<K> od;
-    if (!od.first(T.n_allowed)) return;
-    do {
-        Cand<K> cd;
-#pragma unroll
-        for (int i = 0; i < K; ++i) cd.c[i] = T.allowed[od.pos[i]];
-        float2 X[K + 2];
-        float loss;
-        construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-        const float valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
-        if (valid != 0.0f) {
-            float r;
-            acc = acc + valid * path_value<K>(p, X, r);  // scene.py:1909
-        }
-        if (vrow) vrow[col] = valid;
-        ++col;
-    } while (od.next(T.n_allowed));
+template <int MODE, int METHOD, int K, bool TXGRID>
+__device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
+                                          const float alpha, const float2 fx, const float2 g, const long long col0,
+                                          int& buf, float& acc, float* vrow) {
+    const float2 tx = TXGRID ? g : fx;
+    const float2 rx = TXGRID ? fx : g;
+    for_each_candidate<MODE, METHOD, K, TXGRID>(
+        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col) {
+            if (!tile.active) return;
+            float2 X[K + 2];
+            float loss;
+            construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
+            const float valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+            if (valid != 0.0f) {
+                float r;
+                acc = acc + valid * path_value<K>(p, X, r);  // scene.py:1909
+                if (vrow) vrow[col] = valid;                 // (valid_out is zero-filled by the launcher)
+            }
+        });
 }
 
 template <int MODE, int METHOD, bool TXGRID>
-__global__ void __launch_bounds__(128) power_fwd_kernel(const KParams p, float* __restrict__ Z,
-                                                        float* __restrict__ valid_out) {
+__global__ void __launch_bounds__(kBlock) power_fwd_kernel(const KParams p, float* __restrict__ Z,
+                                                           float* __restrict__ valid_out) {
     extern __shared__ __align__(16) unsigned char smem[];
-    __shared__ int s_count;
+    __shared__ DriverShared sh;
     SceneTab T = carve_tab(smem, p.N);
-    build_tab(T, p, &s_count);
-    const long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (r >= p.R) return;
+    build_tab(T, p, &sh.count);
+    const Tile tile = make_tile(p, T, sh);
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
-    const float2 g = reinterpret_cast<const float2*>(p.grid)[r];
+    const float2 g = tile.active ? reinterpret_cast<const float2*>(p.grid)[tile.r] : make_float2(0.f, 0.f);
     float zsum = 0.0f;
+    int buf = 0;
     for (int t = 0; t < p.T; ++t) {
         const float2 fx = reinterpret_cast<const float2*>(p.fixed)[t];
-        const float2 tx = TXGRID ? g : fx;
-        const float2 rx = TXGRID ? fx : g;
         float acc = 0.0f;  // scene.py:1893
-        long long col = 0;
-        float* vrow = valid_out ? valid_out + ((long long)t * p.R + r) * p.C_total : nullptr;
+        long long col0 = 0;
+        float* vrow = (valid_out && tile.active) ? valid_out + ((long long)t * p.R + tile.r) * p.C_total : nullptr;
         for (int k = p.min_order; k <= p.max_order; ++k) {
             switch (k) {
-                case 0: run_order<MODE, METHOD, 0>(T, p, alpha, tx, rx, acc, vrow, col); break;
-                case 1: run_order<MODE, METHOD, 1>(T, p, alpha, tx, rx, acc, vrow, col); break;
-                case 2: run_order<MODE, METHOD, 2>(T, p, alpha, tx, rx, acc, vrow, col); break;
-                case 3: run_order<MODE, METHOD, 3>(T, p, alpha, tx, rx, acc, vrow, col); break;
-                case 4: run_order<MODE, METHOD, 4>(T, p, alpha, tx, rx, acc, vrow, col); break;
+                case 0: run_order<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
+                case 1: run_order<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
+                case 2: run_order<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
+                case 3: run_order<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
+                case 4: run_order<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
                 default: break;
             }
+            col0 += order_count(k, T.n_allowed);
         }
-        if (p.reduce_all) zsum = zsum + acc;  // scene.py:1939-1952 (0.0 + p0 + p1 ...)
-        else Z[(long long)t * p.R + r] = acc;
+        if (tile.active) {
+            if (p.reduce_all) zsum = zsum + acc;  // scene.py:1939-1952 (0.0 + p0 + p1 ...)
+            else Z[(long long)t * p.R + tile.r] = acc;
+        }
     }
-    if (p.reduce_all) Z[r] = zsum;
+    if (tile.active && p.reduce_all) Z[tile.r] = zsum;
 }
+
+static long long host_tile_blocks(const KParams& p) {
+    if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
+        const long long rows = p.R / p.grid_cols;
+        return (long long)((p.grid_cols + kTileCols - 1) / kTileCols) * ((rows + kTileRows - 1) / kTileRows);
+    }
+    return (p.R + kBlock - 1) / kBlock;
+}
+
+long long num_tile_blocks(const KParams& p) { return host_tile_blocks(p); }
 
 template <int MODE, int METHOD, bool TXGRID>
 static int launch_one(const KParams& p, float* Z, float* valid_out, cudaStream_t stream) {
-    const int block = 128;
-    const long long nblk = (p.R + block - 1) / block;
+    const long long nblk = host_tile_blocks(p);
     const size_t smem = scene_tab_bytes(p.N);
     auto kern = power_fwd_kernel<MODE, METHOD, TXGRID>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<(unsigned)nblk, block, smem, stream>>>(p, Z, valid_out);
+    kern<<<(unsigned)nblk, kBlock, smem, stream>>>(p, Z, valid_out);
     return (int)cudaGetLastError();
 }
 
@@ -104,6 +112,10 @@ static int launch_method(const KParams& p, int grid_role, int method, float* Z, 
 int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, float* Z, float* valid_out,
                      cudaStream_t stream, long long* launches) {
     if (p.R <= 0) return 0;
+    if (valid_out) {
+        const cudaError_t e = cudaMemsetAsync(valid_out, 0, sizeof(float) * (size_t)p.T * p.R * p.C_total, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     int e;
     switch (mode) {
         case D2D_MODE_HARD: e = launch_method<D2D_MODE_HARD>(p, grid_role, method, Z, valid_out, stream); break;

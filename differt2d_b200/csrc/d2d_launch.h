@@ -15,6 +15,8 @@ struct BwdOut {
     float* alpha_bar;    // optional [1]
 };
 
+long long num_tile_blocks(const KParams& p);
+
 // returns cudaError_t as int; *launches incremented by the number of kernels launched
 int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, float* Z, float* valid_out,
                      cudaStream_t stream, long long* launches);

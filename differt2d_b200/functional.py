@@ -40,6 +40,8 @@ class TraceConfig:
     r_coef: float = DEFAULT_R_COEF
     height: float = DEFAULT_HEIGHT
     reduce_all: bool = False
+    grid_cols: int = 0  # row length of a row-major mesh grid (enables 16 x 8 tiles); 0 = unknown
+    cull: bool = True   # tile-level candidate culling (identical results)
 
 
 def _dev_f32(x, device) -> torch.Tensor:
@@ -103,6 +105,8 @@ class _Packed:
         p.r_coef = float(cfg.r_coef)
         p.height = float(cfg.height)
         p.reduce_all = int(cfg.reduce_all)
+        p.grid_cols = int(cfg.grid_cols)
+        p.no_cull = 0 if cfg.cull else 1
         self.p = p
         self.T = self.fixed.shape[0]
         self.R = self.grid.shape[0]

@@ -270,6 +270,9 @@ class Scene:
         fixed = np.stack([fixed_src[k].xy for k in names]) if names else np.zeros((0, 2), np.float32)
         xys, kinds, phis = self.packed_objects()
         x0 = self._x0(cfg, key, device)
+        if len(shape) == 2:
+            import dataclasses
+            cfg = dataclasses.replace(cfg, grid_cols=int(shape[1]))
         back = (lambda t: t.cpu().numpy()) if as_numpy else (lambda t: t.to(Xt.device))
         want_grad = grad or value_and_grad
         if not want_grad:

@@ -75,6 +75,8 @@ typedef struct D2DProblem {
     int64_t n_grid;        /* R = n*m grid points                                                 */
     const float *grid_xy;  /* [R,2] = dstack((X,Y)).reshape(-1,2) (scene.py:1932), row-major n×m  */
     int32_t grid_role;     /* D2D_GRID_*                                                          */
+    int32_t grid_cols;     /* optional: m when the grid is a row-major n x m mesh (X.shape[1]); lets the  */
+                           /* kernels use compact 16 x 8 tiles.  0 = unknown (128 consecutive points).     */
     /* ---- candidates: all_path_candidates (scene.py:122-175) --------------------------------- */
     int32_t min_order, max_order;
     const int32_t *filter_nodes; /* HOST pointer: object indices never visited (scene.py:158-160) */
@@ -96,6 +98,7 @@ typedef struct D2DProblem {
     double height;  /* defaults.py:15   double precision and then cast to f32 (utils.py:52-54)      */
     int32_t reduce_all; /* sum over the fixed points (scene.py:1939-1952)                          */
     int32_t grad_mode;  /* D2D_GRAD_*                                                              */
+    int32_t no_cull;    /* 1 disables the tile-level candidate culling (identical results, slower)        */
 } D2DProblem;
 
 /* Fills a problem with the reference's defaults (defaults.py, geometry.py:915, optimize.py:49,83). */

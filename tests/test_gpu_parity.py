@@ -57,17 +57,22 @@ def test_candidates_device_bit_exact(n, k, f):
     assert np.array_equal(F.candidates(n, k, f), want)  # host odometer of the same library
 
 
+TILINGS = {"flat": dict(grid_cols=0), "tiled": dict(grid_cols=40), "tiled_nocull": dict(grid_cols=40, cull=False)}
+
+
 @pytest.mark.parametrize("name", ["square", "obstacle", "wall", "basic", "geojson", "geojson_norm"])
 @pytest.mark.parametrize("grid_kind", ["bbox", "jitter"])
-def test_hard_masks_and_map_bit_exact(name, grid_kind):
-    """Hard logic: validity of every (receiver, candidate) and the accumulated map, bit for bit."""
+@pytest.mark.parametrize("tiling", list(TILINGS))
+def test_hard_masks_and_map_bit_exact(name, grid_kind, tiling):
+    """Hard logic: validity of every (receiver, candidate) and the accumulated map, bit for bit —
+    with 1-D and 16x8 tiles, with and without the tile-level candidate culling."""
     sc = SCENES[name]
     X, Y = _grid(sc, 48, 40, grid_kind)
     grid = np.stack([X, Y], -1).reshape(-1, 2)
     xys, kinds, phis = sc.packed_objects()
     fixed = np.stack([p.xy for p in sc.transmitters.values()])
     Zo, vo = CO.power_map(xys, fixed, grid, max_order=2, mode="hard", want_valid=True)
-    Z, v = F.power_fwd(_cfg("hard", max_order=2), xys, fixed, grid, want_valid=True, device="cuda")
+    Z, v = F.power_fwd(_cfg("hard", max_order=2, **TILINGS[tiling]), xys, fixed, grid, want_valid=True, device="cuda")
     v = v.cpu().numpy()
     assert np.array_equal(v, vo), f"{int((v != vo).sum())} of {v.size} hard validity flags differ"
     assert np.array_equal(Z.cpu().numpy(), Zo)
@@ -83,7 +88,8 @@ def test_smooth_validity_and_map(name, mode, alpha):
     xys, kinds, phis = sc.packed_objects()
     fixed = np.stack([p.xy for p in sc.transmitters.values()])
     Zo, vo = CO.power_map(xys, fixed, grid, max_order=2, mode=mode, alpha=alpha, want_valid=True)
-    Z, v = F.power_fwd(_cfg(mode, max_order=2), xys, fixed, grid, alpha=alpha, want_valid=True, device="cuda")
+    Z, v = F.power_fwd(_cfg(mode, max_order=2, grid_cols=36), xys, fixed, grid, alpha=alpha, want_valid=True,
+                       device="cuda")
     v = v.cpu().numpy()
     if mode == "hard_sigmoid":
         # same monotone map applied to bit-identical pre-activations: bit-exact
@@ -141,8 +147,8 @@ def test_vjp_against_autograd_oracle(name, mode, alpha, generic):
     xys, kinds, phis = sc.packed_objects()
     fixed = np.stack([p.xy for p in sc.transmitters.values()])
     grid = np.stack([X, Y], -1).reshape(-1, 2)
-    out = F.power_bwd(_cfg(mode, max_order=2, reduce_all=True), xys, fixed, grid, Zbar.reshape(-1), alpha=alpha,
-                      device="cuda")
+    out = F.power_bwd(_cfg(mode, max_order=2, reduce_all=True, grid_cols=X.shape[1]), xys, fixed, grid,
+                      Zbar.reshape(-1), alpha=alpha, device="cuda")
     out = {k: v.cpu().numpy() for k, v in out.items()}
     np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
     _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar")
@@ -208,3 +214,38 @@ def test_autograd_function_matches_direct_vjp():
     assert torch.allclose(xy_t.grad, ref["objects"], rtol=1e-3, atol=1e-3 * ref["objects"].abs().max().item())
     assert torch.allclose(grid.grad, ref["grid"].reshape(-1, 2), rtol=1e-5, atol=1e-6)
     assert torch.allclose(alpha.grad.reshape(1), ref["alpha"], rtol=1e-3)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_large_grid_cull_equals_nocull(mode):
+    """Size-independent property at a benchmark-like size: the tile cull never changes a bit of the map
+    (512 x 512 receivers x 785 candidates on the normalised city scene), nor of the reverse-mode outputs."""
+    sc = SCENES["geojson_norm"]
+    X, Y = sc.grid(512, 512)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    a = F.power_fwd(_cfg(mode, max_order=2, grid_cols=512), xys, fixed, grid, alpha=100.0, device="cuda")
+    b = F.power_fwd(_cfg(mode, max_order=2, grid_cols=512, cull=False), xys, fixed, grid, alpha=100.0, device="cuda")
+    c = F.power_fwd(_cfg(mode, max_order=2, grid_cols=0, cull=False), xys, fixed, grid, alpha=100.0, device="cuda")
+    assert torch.equal(a, b) and torch.equal(a, c)
+    ga = F.power_bwd(_cfg(mode, max_order=2, grid_cols=512, reduce_all=True), xys, fixed, grid, None, alpha=100.0,
+                     want=("Z", "grid"), device="cuda")
+    gb = F.power_bwd(_cfg(mode, max_order=2, grid_cols=512, reduce_all=True, cull=False), xys, fixed, grid, None,
+                     alpha=100.0, want=("Z", "grid"), device="cuda")
+    assert torch.equal(ga["Z"], gb["Z"]) and torch.equal(ga["grid"], gb["grid"])
+    assert torch.equal(ga["Z"], a.reshape(-1))
+
+
+def test_raw_geojson_cull_equals_nocull():
+    """Same property on the raw lon/lat coordinates (fp32-degenerate): the error-aware
+    tolerance of the cull must keep it conservative there too."""
+    sc = SCENES["geojson"]
+    X, Y = sc.grid(256, 256)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    for mode in MODES:
+        a = F.power_fwd(_cfg(mode, max_order=2, grid_cols=256), xys, fixed, grid, alpha=100.0, device="cuda")
+        b = F.power_fwd(_cfg(mode, max_order=2, grid_cols=256, cull=False), xys, fixed, grid, alpha=100.0, device="cuda")
+        assert torch.equal(a, b), mode
