@@ -104,7 +104,7 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
 // and must satisfy min(s, 1 - s) > xz with s its parametric coordinate on the last object (geometry.py:
 // 595-621), xz = x_zero<MODE>.  Returns false only if NO point of the box can satisfy it.
 __device__ __forceinline__ bool tile_may_reach(const float2 apex, const float4 w0, const float4 w1, const int kind,
-                                               const float4 bbox, const float scale, const float xz) {
+                                               const float4 bbox, const float scale, const float xz, const float p_tolscale) {
     if (kind == D2D_KIND_VERTEX) return true;
     if (!(xz > -CUDART_INF_F)) return true;
     const float qx[4] = {bbox.x, bbox.z, bbox.x, bbox.z};
@@ -132,10 +132,11 @@ __device__ __forceinline__ bool tile_may_reach(const float2 apex, const float4 w
     }
     if (!(pos == 4 || neg == 4)) return true;   // the denominator may vanish inside the box
     if (!(smin == smin) || !(smax == smax)) return true;
-    // fp32 error of the exact evaluation: err(X) <~ 16 eps S (|g| + |u|/|un| + |g||u|/|un|), 8x safety
+    // fp32 error of the exact evaluation, first order: the image carries ~2K eps S, so
+    // err(X) <~ 4 eps S (|g| + |u|/|un| + |g||u|/|un|) + eps S; 16 eps S (...) is used, times p_tolscale (4)
     const float eps = 5.9604645e-8f;
     const float tolX = 16.0f * eps * scale * (gmax + umax / unmin + Gmax / unmin) + 4.0f * eps * (scale + Gmax);
-    const float tol = 1e-4f + 8.0f * tolX / sqrtf(w1.z);
+    const float tol = 1e-4f + p_tolscale * tolX / sqrtf(w1.z);
     if (!(tol < CUDART_INF_F)) return true;
     const float lo = xz - tol, hi = 1.0f - xz + tol;
     return !(smax < lo || smin > hi);
@@ -200,7 +201,7 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
 #pragma unroll
                 for (int i = 0; i < K; ++i) I = mirror(I, T.w0[c[i]], T.w1[c[i]]);
                 const int j = c[K - 1];
-                keep = tile_may_reach(I, T.w0[j], T.w1[j], T.kind[j], tile.bbox, tile.scale, xz);
+                keep = tile_may_reach(I, T.w0[j], T.w1[j], T.kind[j], tile.bbox, tile.scale, xz, (float)p.cull);
             }
         }
         // ordered compaction: per-warp segments keep list order

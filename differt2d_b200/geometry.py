@@ -97,7 +97,7 @@ class RIS(Wall):
 
 
 class Path:
-    """geometry.py:724-973 — tag: every object sampled at t = 0.5 (not fused; use the oracle for plots)."""
+    """geometry.py:724-973 — base tag (every object sampled at t = 0.5 in the reference; not fused here)."""
 
     METHOD = None
 

@@ -1,0 +1,135 @@
+"""CPU tests of the host mirror (Scene container, builders, keyword resolution) and of the multi-GPU
+plumbing with the gloo backend at world_size 2."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+import differt2d_b200 as d
+from differt2d_b200 import distributed as D
+from differt2d_b200 import logic
+from oracle import ref_torch as R
+from tests import helpers as H
+
+
+def test_builders_match_oracle_scenes():
+    for a, b in [(d.Scene.square_scene(), R.square_scene()), (d.Scene.basic_scene(), R.basic_scene()),
+                 (d.Scene.square_scene_with_wall(), R.square_scene_with_wall()),
+                 (d.Scene.square_scene_with_obstacle(), R.square_scene_with_obstacle())]:
+        xys, kinds, phis = a.packed_objects()
+        assert np.array_equal(xys, b.xys.numpy()) and kinds.tolist() == b.kinds
+        assert np.array_equal(a.transmitters["tx"].xy, b.transmitters["tx"].numpy())
+        assert np.array_equal(a.receivers["rx"].xy, b.receivers["rx"].numpy())
+
+
+def test_from_geojson(geojson_rings):
+    """tests/test_scene.py:217-253 of the reference"""
+    sc = d.Scene.from_geojson(H.geojson_text())
+    assert len(sc.objects) == 28 and all(isinstance(o, d.Wall) for o in sc.objects)
+    osc = R.scene_from_geojson_rings(geojson_rings)
+    assert np.array_equal(sc.packed_objects()[0], osc.xys.numpy())
+    assert np.array_equal(sc.transmitters["tx"].xy, osc.transmitters["tx"].numpy())
+    assert np.array_equal(sc.receivers["rx"].xy, osc.receivers["rx"].numpy())
+    empty = d.Scene.from_geojson(json.dumps({"features": []}))
+    assert len(empty.objects) == 0 and empty.receivers["rx"].xy.tolist() == [1.0, 1.0]
+
+
+def test_grid_shapes():
+    """tests/test_abc.py:10-29 — grid(m, n) has shape (n, m); grid(m) is square"""
+    sc = d.Scene.basic_scene()
+    X, Y = sc.grid(300, 50)
+    assert X.shape == (50, 300) and Y.shape == (50, 300) and X.dtype == np.float32
+    X, Y = sc.grid(25)
+    assert X.shape == (25, 25)
+    assert np.allclose(sc.center(), [0.5, 0.5])
+    assert sc.get_location("NW").tolist() == [0.0, 1.0] and sc.get_location("SE").tolist() == [1.0, 0.0]
+
+
+def test_candidates_api():
+    """tests/test_scene.py:372-399 of the reference, through the product API (host enumerator of the .so)"""
+    sc = d.Scene.random_uniform_scene(key=1234, n_receivers=10, n_walls=11)
+    got = sc.all_path_candidates(min_order=0, max_order=0, device=None)
+    assert len(got) == 1 and len(got[0]) == 0
+    sc = d.Scene(objects=[d.Wall(), d.Wall(), d.Wall()]).add_objects(d.RIS(), d.Wall(), d.Wall())
+    got = sc.all_path_candidates(filter_objects=lambda o: isinstance(o, d.RIS), min_order=0, max_order=2)
+    assert [c.tolist() for c in got] == [[], [3]] and all(c.dtype == np.int32 for c in got)
+
+
+def test_mode_resolution():
+    assert logic.resolve_mode(False) == "hard"
+    assert logic.resolve_mode(True) == "hard_sigmoid"  # logic.py:266 default activation
+    assert logic.resolve_mode(True, logic.sigmoid) == "sigmoid"
+    with logic.enable_approx(True):
+        assert logic.resolve_mode(None) == "hard_sigmoid"
+    with logic.disable_approx():
+        assert logic.resolve_mode(None) == "hard"
+    with pytest.raises(NotImplementedError):
+        logic.resolve_mode(True, lambda x, a: x)
+
+
+def test_unsupported_requests_raise():
+    sc = d.Scene.square_scene()
+    X, Y = sc.grid(4)
+    with pytest.raises(NotImplementedError):
+        sc._config("receivers", lambda *a: 0.0, (), None, False, d.ImagePath, None, 0, 1, None, None, {})
+    with pytest.raises(NotImplementedError):
+        sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"many": 3}, 0, 1, None, None, {})
+    with pytest.raises(TypeError):
+        sc._config("receivers", d.received_power, (), None, False, d.ImagePath, None, 0, 1, None, None, {"bogus": 1})
+    with pytest.raises(TypeError):
+        sc.add_objects(d.Vertex(xy=[0.3, 0.3]))._config("receivers", d.received_power, (), None, False, d.ImagePath,
+                                                        None, 0, 1, None, None, {})
+    cfg, alpha = sc._config("receivers", d.received_power, (), {"r_coef": 0.3, "height": 0.0}, True, d.FermatPath,
+                            {"steps": 7}, 0, 1, 2, None, {"approx": True, "alpha": 12.0, "tol": 0.5})
+    assert (cfg.min_order, cfg.max_order, cfg.steps, cfg.r_coef, cfg.height, cfg.mode, cfg.tol) == \
+           (2, 2, 7, 0.3, 0.0, "hard_sigmoid", 0.5) and alpha == 12.0
+
+
+def test_row_blocks_partition_the_grid():
+    for n in (1, 7, 10, 1024, 2048):
+        for w in (1, 2, 3, 4, 8):
+            blocks = [D.row_block(n, w, r) for r in range(w)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(blocks[:-1], blocks[1:]))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_pack_unpack_roundtrip():
+    o, ph, f, a = torch.randn(5, 2, 2), torch.randn(5), torch.randn(3, 2), torch.randn(1)
+    buf = D.pack_param_grads(o, ph, f, a)
+    assert buf.numel() == 5 * 4 + 5 + 3 * 2 + 1  # 4N + N + 2T + 1 floats
+    o2, ph2, f2, a2 = D.unpack_param_grads(buf, 5, 3)
+    assert torch.equal(o, o2) and torch.equal(ph, ph2) and torch.equal(f, f2) and torch.equal(a, a2)
+
+
+def _gloo_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    D.init(world, rank, backend="gloo")
+    # every rank owns a row block; parameter cotangents are partial sums -> one all-reduce
+    n = 9
+    r0, r1 = D.row_block(n, world, rank)
+    full = torch.arange(n * 4, dtype=torch.float32).reshape(n, 4)
+    part = D.pack_param_grads(full[r0:r1].sum(0).reshape(1, 2, 2), torch.tensor([float(rank)]),
+                              torch.tensor([[1.0, 2.0]]) * (rank + 1), torch.tensor([0.5]))
+    D.allreduce_sum_(part)
+    tmax = D.max_over_ranks(10.0 + rank, "cpu")
+    D.barrier()
+    if rank == 0:
+        torch.save({"buf": part, "tmax": tmax}, out)
+    D.shutdown()
+
+
+def test_gloo_world_size_2_allreduce(tmp_path):
+    out = str(tmp_path / "r0.pt")
+    port = 29500 + (os.getpid() % 2000)
+    mp.spawn(_gloo_worker, args=(2, port, out), nprocs=2, join=True)
+    res = torch.load(out)
+    full = torch.arange(9 * 4, dtype=torch.float32).reshape(9, 4)
+    o, ph, f, a = D.unpack_param_grads(res["buf"], 1, 1)
+    assert torch.equal(o.reshape(-1), full.sum(0))          # sum over both row blocks == full-grid sum
+    assert ph.item() == 1.0 and f.tolist() == [[3.0, 6.0]] and a.item() == 1.0
+    assert res["tmax"] == 11.0

@@ -1,0 +1,295 @@
+"""
+Pins the oracle (oracle/ref_torch.py and oracle/d2d_oracle.c) against the known-answer tests the
+REFERENCE's own test-suite and doctests hold for this path.  Each test cites the
+reference test it restates (paths relative to /root/reference).  CPU only.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import c_oracle as CO
+from oracle import ref_torch as R
+
+APPROX = [False, True]
+
+
+def T(x):
+    return torch.tensor(x, dtype=torch.float32)
+
+
+@pytest.mark.parametrize("approx", APPROX)
+def test_segments_intersect(approx):
+    """tests/test_geometry.py:101-120 and doctest geometry.py:139-151"""
+    L = R.Logic(approx)
+    hit = R.segments_intersect(T([0.0, 0.0]), T([1.0, 0.0]), T([0.5, -1.0]), T([0.5, 1.0]), L)
+    assert bool(L.is_true(hit))
+    if approx:
+        assert float(hit) == 1.0
+        assert float(R.segments_intersect(T([0.0, 0.0]), T([1.0, 0.0]), T([0.5, -1.0]), T([0.5, 1.0]),
+                                          R.Logic(True, function="sigmoid"))) == 1.0
+    miss = R.segments_intersect(T([0.0, 0.0]), T([1.0, 0.0]), T([0.0, 1.0]), T([1.0, 1.0]), L)
+    assert bool(L.is_false(miss))
+
+
+def test_path_length():
+    """tests/test_geometry.py:123-135 (== 4.0 exactly despite eps) and doctest geometry.py:193-197"""
+    sq = T([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 1.0], [0.0, 0.0]])
+    assert float(R.path_length(sq)) == 4.0
+    tri = T([[0.0, 0.0], [1.0, 0.0], [1.0, 1.0], [0.0, 0.0]])
+    assert np.float32(R.path_length(tri).item()) == np.float32(3.4142137)
+
+
+def test_normalize():
+    """doctest geometry.py:217-225"""
+    v, l = R.normalize(T([1.0, 1.0]))
+    assert np.allclose(v.numpy(), [0.70710677, 0.70710677]) and np.float32(l.item()) == np.float32(1.4142135)
+    v, l = R.normalize(T([0.0, 0.0]))
+    assert v.tolist() == [0.0, 0.0] and float(l) == 1.0
+
+
+@pytest.mark.parametrize("origin,dest", [([0.0, 0.0], [1.0, 0.0]), ([0.0, 0.0], [0.0, 1.0]),
+                                         ([0.3, 0.2], [4.0, 2.0]), ([1.0, 1.0], [-2.0, 0.5])])
+def test_wall_normal(origin, dest):
+    """tests/test_geometry.py:256-261"""
+    sc = R.OScene([[origin, dest]])
+    n = sc.normal(0)
+    v = T(dest) - T(origin)
+    assert abs(float(R.dot2(v, n))) < 1e-6
+    assert abs(float(R.norm2(n)) - 1.0) < 1e-6
+
+
+def test_wall_parametric():
+    """tests/test_geometry.py:268-322"""
+    sc = R.OScene([[[0.0, 0.0], [4.0, 2.0]]])
+    assert sc.parametric_to_cartesian(0, T(0.5)).tolist() == [2.0, 1.0]
+    for p, want in [([2.0, 1.0], 0.5), ([0.0, 0.0], 0.0), ([4.0, 2.0], 1.0), ([8.0, 4.0], 2.0), ([-4.0, -2.0], -1.0)]:
+        assert float(sc.cartesian_to_parametric(0, T(p))) == want
+    for approx in APPROX:
+        L = R.Logic(approx)
+        assert bool(L.is_true(sc.contains_parametric(0, T(0.5), L)))
+        assert bool(L.is_false(sc.contains_parametric(0, T(2.0), L)))
+
+
+@pytest.mark.parametrize("approx", APPROX)
+def test_wall_intersects_cartesian(approx):
+    """tests/test_geometry.py:324-342 incl. 'intersects on the extremity'"""
+    sc = R.OScene([[[0.0, 0.0], [4.0, 2.0]]])
+    L = R.Logic(approx)
+    assert bool(L.is_true(sc.intersects_cartesian(0, T([0.0, 2.0]), T([4.0, 0.0]), L)))
+    assert bool(L.is_false(sc.intersects_cartesian(0, T([0.0, 1.0]), T([4.0, 3.0]), L)))
+    assert bool(L.is_false(sc.intersects_cartesian(0, T([0.0, 1.0]), T([2.0, 7.0]), L)))
+    got = sc.intersects_cartesian(0, T([0.0, 1.0]), T([0.0, 0.0]), L)
+    assert float(got) > 0 if approx else bool(got)
+
+
+def test_evaluate_cartesian():
+    """tests/test_geometry.py:344-355 (Wall, specular = 0) and :365-376 (RIS, phi = 0)"""
+    sc = R.OScene([[[0.0, 0.0], [4.0, 0.0]]])
+    assert abs(float(sc.evaluate_cartesian(0, T([0.0, 1.0]), T([2.0, 0.0]), T([4.0, 1.0])))) < 1e-6
+    assert abs(float(sc.evaluate_cartesian(0, T([0.0, 1.0]), T([2.1, 0.0]), T([4.0, 1.0])))) > 1e-4
+    ris = R.OScene([[[0.0, 0.0], [4.0, 0.0]]], kinds=[R.KIND_RIS], phis=[0.0])
+    assert abs(float(ris.evaluate_cartesian(0, T([0.0, 1.0]), T([2.0, 0.0]), T([2.0, 1.0])))) < 1e-6
+    assert abs(float(ris.evaluate_cartesian(0, T([0.0, 1.0]), T([2.0, 0.0]), T([4.0, 1.0])))) > 1e-4
+
+
+def test_image_of():
+    """doctest geometry.py:663-667"""
+    sc = R.OScene([[[0.0, 0.0], [1.0, 0.0]]])
+    assert sc.image_of(0, T([0.0, 1.0])).tolist() == [0.0, -1.0]
+
+
+def test_path_sampled_at_half():
+    """tests/test_geometry.py:380-399"""
+    sc = R.OScene([[[0.0, 0.0], [2.0, 0.0]]])
+    pts, _ = R.from_tx_objects_rx(sc, "path", T([0.0, 1.0]), [0], T([2.0, 1.0]))
+    assert abs(float(R.path_length(R._stack_pts(pts))) - 2 * math.sqrt(2)) < 1e-6
+    for method in ("path", "image", "fermat", "minpath"):
+        pts, _ = R.from_tx_objects_rx(sc, method, T([0.0, 1.0]), [], T([2.0, 1.0]), x0=np.zeros(1, np.float32))
+        assert abs(float(R.path_length(R._stack_pts(pts))) - 2.0) < 1e-6
+
+
+@pytest.mark.parametrize("approx", APPROX)
+@pytest.mark.parametrize("method", ["image", "fermat", "minpath"])
+def test_is_valid_square_scene(approx, method):
+    """tests/test_geometry.py:451-467 — candidate [0,1,2,3] on square_scene is valid for every path class"""
+    sc = R.square_scene()
+    L = R.Logic(approx)
+    x0 = np.random.default_rng(1234).random(4, dtype=np.float32)
+    pts, loss = R.from_tx_objects_rx(sc, method, sc.transmitters["tx"], [0, 1, 2, 3], sc.receivers["rx"], x0=x0,
+                                     steps=100)
+    assert bool(L.is_true(R.is_valid(sc, [0, 1, 2, 3], pts, loss, L)))
+
+
+def test_image_path_loss_is_zero():
+    """tests/test_geometry.py:492-500 (atol 1e-13)"""
+    sc = R.square_scene()
+    _, loss = R.image_path(sc, sc.transmitters["tx"], [0, 1, 2, 3], sc.receivers["rx"])
+    assert abs(float(loss)) <= 1e-13
+
+
+@pytest.mark.parametrize("method", ["fermat", "minpath"])
+def test_solver_simple_reflection(method):
+    """tests/test_geometry.py:503-525 — single reflection hits (1, 0), rtol 1e-2; MinPath loss atol 1e-4"""
+    sc = R.OScene([[[0.0, 0.0], [2.0, 0.0]]])
+    x0 = np.random.default_rng(1234).random(1, dtype=np.float32)
+    pts, loss = R.from_tx_objects_rx(sc, method, T([0.0, 1.0]), [0], T([2.0, 1.0]), x0=x0, steps=100)
+    got = torch.stack([p.reshape(2) for p in pts]).numpy()
+    np.testing.assert_allclose(got, [[0.0, 1.0], [1.0, 0.0], [2.0, 1.0]], rtol=1e-2, atol=1e-2)
+    if method == "minpath":
+        assert abs(float(loss)) < 1e-4
+
+
+def test_minimize_quadratic():
+    """tests/test_optimize.py:27-74 and doctest optimize.py:67-81"""
+    x, y = R.minimize_adam(lambda x: ((x - 1.0) ** 2).sum(-1), torch.zeros(10), steps=1000)
+    np.testing.assert_allclose(x.numpy(), np.ones(10), rtol=1e-3)
+    x, y = R.minimize_adam(lambda x: ((x - 1.0) ** 2).sum(-1), torch.zeros(10), steps=100)
+    np.testing.assert_allclose(x.numpy(), np.ones(10), rtol=1e-2)
+    assert abs(float(y)) < 1e-4
+
+
+def test_received_power():
+    """tests/test_utils.py:8-22 — 0.3 / 4"""
+    pts = [T([0.0, 0.0]), T([1.0, 0.0]), T([1.0, 1.0])]
+    assert abs(float(R.received_power(pts, r_coef=0.3, height=0.0)) - 0.3 / 4.0) < 1e-6
+
+
+@pytest.mark.parametrize("alpha", [1e-3, 1e-2, 1e-1, 1.0, 10.0])
+def test_activation(alpha):
+    """tests/test_logic.py:208-218"""
+    x = torch.linspace(-5, 5, 200)
+    np.testing.assert_allclose(R.Logic(True, alpha, "sigmoid").activation(x).numpy(),
+                               (1 / (1 + np.exp(-alpha * x.numpy().astype(np.float64)))), rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(R.Logic(True, alpha, "hard_sigmoid").activation(x).numpy(),
+                               np.clip(alpha * x.numpy() + 3, 0, 6) / 6, rtol=1e-6, atol=1e-7)
+
+
+def test_logic_ops():
+    """tests/test_logic.py:221-386"""
+    rng = np.random.default_rng(0)
+    x, y = T(rng.random(200)), T(rng.random(200))
+    Ls, Lh = R.Logic(True), R.Logic(False)
+    assert torch.equal(Ls.lor(x, y), torch.maximum(x, y)) and torch.equal(Ls.land(x, y), torch.minimum(x, y))
+    assert torch.equal(Ls.lnot(x), 1.0 - x)
+    assert torch.equal(Lh.ge(x, y), x >= y) and torch.equal(Lh.lt(x, y), x < y) and torch.equal(Lh.le(x, y), x <= y)
+    assert torch.equal(Ls.ge(x, y), Ls.activation(x - y)) and torch.equal(Ls.lt(x, y), Ls.activation(y - x))
+    assert float(Ls.lall(T(0.2), T(0.7), T(0.5))) == pytest.approx(0.2)
+    assert float(Ls.lany(T(0.2), T(0.7), T(0.5))) == pytest.approx(0.7)
+    assert float(Ls.true_value()) == 1.0 and float(Ls.false_value()) == 0.0
+    assert bool(Lh.true_value()) is True and bool(Lh.false_value()) is False
+
+
+def test_candidates_kats():
+    """tests/test_scene.py:372-399: order 0 -> one empty candidate; filter -> [[], [3]]; plus differt-core's
+    documented lexicographic example (3 nodes, order 2)."""
+    for impl in (R.all_path_candidates, CO.all_path_candidates):
+        got = impl(11, min_order=0, max_order=0)
+        assert len(got) == 1 and len(got[0]) == 0
+        got = impl(11, order=0)
+        assert len(got) == 1 and len(got[0]) == 0
+        got = impl(6, min_order=0, max_order=2, filter_nodes=(0, 1, 2, 4, 5))
+        assert [c.tolist() for c in got] == [[], [3]]
+        assert all(c.dtype == np.int32 for c in got)
+        got = impl(3, order=2)
+        assert [c.tolist() for c in got] == [[0, 1], [0, 2], [1, 0], [1, 2], [2, 0], [2, 1]]
+        for c in impl(5, min_order=0, max_order=3):
+            assert all(a != b for a, b in zip(c[:-1], c[1:]))  # no self loops
+
+
+def test_accumulate_over_paths_los():
+    """tests/test_scene.py:443-485 — LOS with fun = length**2 gives 2, 1, 1, 2 and 6 in total"""
+    sc = R.OScene(np.zeros((0, 2, 2), np.float32), transmitters={"tx0": [0.0, 0.0], "tx1": [1.0, 0.0]})
+    rx = np.array([[1.0, 1.0], [0.0, 1.0]], np.float32)
+    res = R.accumulate_on_grid(sc, rx[:, 0], rx[:, 1], fun="length_squared", max_order=1, approx=False)
+    vals = [v.tolist() for _, v in res]
+    np.testing.assert_allclose(vals, [[2.0, 1.0], [1.0, 2.0]], rtol=1e-6)
+    Zc = CO.power_map(np.zeros((0, 2, 2), np.float32), [[0.0, 0.0], [1.0, 0.0]], rx, fun="length_squared", max_order=1)
+    np.testing.assert_allclose(Zc, [[2.0, 1.0], [1.0, 2.0]], rtol=1e-6)
+    assert float(Zc.sum()) == pytest.approx(6.0)
+
+
+@pytest.mark.parametrize("role", ["receivers", "transmitters"])
+def test_grid_methods_los(role):
+    """tests/test_scene.py:487-627 — Z = X^2 + Y^2, grad = [2X, 2Y] on the last axis, value_and_grad tuple,
+    results keyed by the fixed points' names in order, reduce_all sums them."""
+    fixed = {"a": [0.0, 0.0], "b": [0.0, 0.0]}
+    sc = R.OScene(np.zeros((0, 2, 2), np.float32), transmitters=fixed, receivers=fixed)
+    x = np.linspace(-2, 2, 9, dtype=np.float32)
+    y = np.linspace(-1, 3, 7, dtype=np.float32)
+    X, Y = np.meshgrid(x, y)
+    res = R.accumulate_on_grid(sc, X, Y, grid_role=role, fun="length_squared", approx=False)
+    assert [k for k, _ in res] == ["a", "b"]
+    for _, Z in res:
+        assert Z.shape == X.shape and Z.dtype == torch.float32
+        np.testing.assert_allclose(Z.numpy(), X * X + Y * Y, rtol=1e-5, atol=1e-6)
+    Z = R.accumulate_on_grid(sc, X, Y, grid_role=role, fun="length_squared", approx=False, reduce_all=True)
+    np.testing.assert_allclose(Z.numpy(), 2 * (X * X + Y * Y), rtol=1e-5, atol=1e-6)
+    for _, dZ in R.accumulate_on_grid(sc, X, Y, grid_role=role, fun="length_squared", approx=False, grad=True):
+        np.testing.assert_allclose(dZ.numpy(), np.stack([2 * X, 2 * Y], -1), rtol=1e-4, atol=1e-5)
+    for _, (Z, dZ) in R.accumulate_on_grid(sc, X, Y, grid_role=role, fun="length_squared", approx=False,
+                                            value_and_grad=True):
+        np.testing.assert_allclose(Z.numpy(), X * X + Y * Y, rtol=1e-5, atol=1e-6)
+        assert dZ.shape == (*X.shape, 2)
+
+
+def test_geojson_scene(geojson_rings):
+    """tests/test_scene.py:217-253 — 28 walls; tx / rx on the NW / SE corners of the bounding box"""
+    sc = R.scene_from_geojson_rings(geojson_rings)
+    assert sc.n == 28
+    bb = sc.bounding_box().numpy()
+    assert sc.transmitters["tx"].tolist() == [bb[0, 0], bb[1, 1]]
+    assert sc.receivers["rx"].tolist() == [bb[1, 0], bb[0, 1]]
+    lens = (sc.xys[:, 1] - sc.xys[:, 0]).abs().sum(-1)
+    assert int((lens == 0).sum()) == 2  # one closure wall per ring (scene.py:646-652)
+
+
+def test_canned_scenes():
+    """doctests scene.py:750-759, 804-813, 856-865, 901-910 (object counts, default end points)"""
+    assert R.basic_scene().n == 7 and R.basic_scene().transmitters["tx"].tolist() == pytest.approx([0.1, 0.1])
+    assert R.square_scene().n == 4 and R.square_scene().receivers["rx"].tolist() == pytest.approx([0.5, 0.6])
+    assert R.square_scene_with_wall().n == 5
+    assert R.square_scene_with_obstacle().n == 8
+
+
+@pytest.mark.parametrize("mode,approx,fn", [("hard", False, "hard_sigmoid"), ("hard_sigmoid", True, "hard_sigmoid")])
+@pytest.mark.parametrize("scene", ["obstacle", "basic"])
+def test_two_oracles_agree_bit_for_bit(mode, approx, fn, scene):
+    """The two independent restatements (vectorised torch, scalar C) must produce identical bits for the
+    validity of every (receiver, candidate), every path value and the accumulated map."""
+    sc = {"obstacle": R.square_scene_with_obstacle, "basic": R.basic_scene}[scene]()
+    X, Y = sc.grid(24, 20)
+    grid = np.stack([X.numpy(), Y.numpy()], -1)
+    tx = sc.transmitters["tx"]
+    Zc, vc, fc = CO.power_map(sc.xys.numpy(), tx.numpy()[None], grid, max_order=2, mode=mode, want_valid=True,
+                              want_fun=True)
+    _, vt, ft = R.valid_masks(sc, tx, torch.from_numpy(grid), max_order=2, approx=approx, function=fn)
+    Zt = R.accumulate_on_grid(sc, X, Y, max_order=2, approx=approx, function=fn)[0][1]
+    assert np.array_equal(vc[0].reshape(20, 24, -1), vt.float().numpy())
+    assert np.array_equal(fc[0].reshape(20, 24, -1), ft.numpy())
+    assert np.array_equal(Zc[0].reshape(20, 24), Zt.numpy())
+
+
+def test_literal_and_vectorised_occlusion_agree():
+    sc = R.basic_scene()
+    X, Y = sc.grid(9, 7)
+    grid = torch.stack((X, Y), -1)
+    for approx in APPROX:
+        L = R.Logic(approx, 10.0)
+        for cand in ([], [0], [4, 1], [2, 6]):
+            pts, _ = R.image_path(sc, sc.transmitters["tx"], cand, grid)
+            a = R.intersects_with_objects(sc, cand, pts, L)
+            b = R.intersects_with_objects(sc, cand, pts, L, literal=True)
+            assert torch.equal(a.expand(7, 9), b.expand(7, 9))
+
+
+def test_clean_gradients_leave_values_unchanged_and_finite():
+    sc = R.square_scene_with_obstacle()
+    X, Y = sc.grid(8, 8)  # includes receivers ON the walls: the literal gradient is NaN there
+    Z0, g0 = R.power_map_and_vjp(sc, X, Y, max_order=1)
+    with R.clean_gradients():
+        Z1, g1 = R.power_map_and_vjp(sc, X, Y, max_order=1)
+    assert torch.equal(Z0, Z1)
+    assert torch.isnan(g0["grid"]).any()
+    assert all(torch.isfinite(v).all() for v in g1.values())
