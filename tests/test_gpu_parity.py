@@ -298,8 +298,12 @@ def test_solver_paths_vertex_scene(method, mode):
     # a flipped borderline flag (loss ~ tol, s ~ 0 or 1) changes the map at that receiver: 50 candidates per
     # receiver x <0.5 % flips -> a few % of the receivers; everywhere else the maps agree to ~1e-6
     assert close.mean() > 0.96, f"only {close.mean():.4f} of the map within tolerance"
+    # receivers whose 50 flags all agree exactly (every activation saturated on both sides) only see the
+    # second-order effect of the iterate noise on the path length: there the maps must agree tightly
+    same = (v == vo).all(-1)
+    assert same.mean() > 0.5, f"only {same.mean():.4f} of the receivers have identical flags"
     tight = np.isclose(Z.cpu().numpy()[0], Zo, rtol=1e-4, atol=1e-5)
-    assert tight.mean() > 0.85, f"only {tight.mean():.4f} of the map within 1e-4"
+    assert tight[same].mean() > 0.99, f"only {tight[same].mean():.4f} of the flag-identical receivers within 1e-4"
 
 
 def test_minpath_ris_scene():
