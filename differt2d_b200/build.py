@@ -4,7 +4,7 @@ IN-TREE with nvcc, so that the shared object travels to the GPU box with the rep
 
     python -m differt2d_b200.build [--force] [--verbose]
 
-The two kernel translation units are compiled with `-fmad=false` (see csrc/d2d_device.cuh,
+The kernel translation units (one per source and logic mode) are compiled with `-fmad=false` (see csrc/d2d_device.cuh,
 "Arithmetic discipline"); FMAs are requested explicitly where wanted.
 """
 
@@ -22,11 +22,10 @@ LIB = os.path.join(OUT_DIR, "libdiffert2d_b200.so")
 
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-prec-div=true", "-prec-sqrt=true", "-ftz=false"]
-UNITS = {
-    "d2d_forward.cu": ["-fmad=false"],
-    "d2d_backward.cu": ["-fmad=false"],
-    "d2d_abi.cu": [],
-}
+# (source, object, extra flags): the kernel sources are compiled once per logic mode, in parallel
+UNITS = [("d2d_forward.cu", f"d2d_forward_m{m}.o", ["-fmad=false", f"-DD2D_TU_MODE={m}"]) for m in (1, 0, 2)]
+UNITS += [("d2d_backward.cu", f"d2d_backward_m{m}.o", ["-fmad=false", f"-DD2D_TU_MODE={m}"]) for m in (1, 0, 2)]
+UNITS += [("d2d_abi.cu", "d2d_abi.o", [])]
 
 
 def _nvcc() -> str:
@@ -60,8 +59,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     objs = []
 
     def compile_one(item):
-        src, extra = item
-        obj = os.path.join(OUT_DIR, src.replace(".cu", ".o"))
+        src, objname, extra = item
+        obj = os.path.join(OUT_DIR, objname)
         cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
@@ -73,8 +72,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
             print(r.stderr, flush=True)
         return obj
 
-    with cf.ThreadPoolExecutor(max_workers=len(UNITS)) as ex:
-        objs = list(ex.map(compile_one, UNITS.items()))
+    with cf.ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as ex:
+        objs = list(ex.map(compile_one, UNITS))
     cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "--cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:

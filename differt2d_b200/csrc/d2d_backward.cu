@@ -433,10 +433,12 @@ __global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, cons
     }
 }
 
+static long long bwd_tile_blocks(const KParams& p);
+
 template <int MODE, bool TXGRID>
 static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out, cudaStream_t stream) {
     const int block = kBlock;
-    const long long nblk = num_tile_blocks(p);
+    const long long nblk = bwd_tile_blocks(p);
     size_t smem = ((scene_tab_bytes(p.N) + 15) / 16) * 16;
     if (out.objects_bar || out.phis_bar) smem += (size_t)5 * p.N * sizeof(float);
     auto kern = power_bwd_kernel<MODE, TXGRID>;
@@ -448,6 +450,27 @@ static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out
     return (int)cudaGetLastError();
 }
 
+#ifndef D2D_TU_MODE
+#error "compile with -DD2D_TU_MODE=<D2D_MODE_*> (differt2d_b200/build.py)"
+#endif
+
+static long long bwd_tile_blocks(const KParams& p) {
+    if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
+        const long long rows = p.R / p.grid_cols;
+        return (long long)((p.grid_cols + kTileCols - 1) / kTileCols) * ((rows + kTileRows - 1) / kTileRows);
+    }
+    return (p.R + kBlock - 1) / kBlock;
+}
+
+template <>
+int launch_bwd_mode<D2D_TU_MODE>(const KParams& p, int grid_role, int method, const float* Zbar, const BwdOut& out,
+                                 cudaStream_t stream) {
+    (void)method;
+    return grid_role == D2D_GRID_TRANSMITTERS ? launch_bwd_one<D2D_TU_MODE, true>(p, Zbar, out, stream)
+                                              : launch_bwd_one<D2D_TU_MODE, false>(p, Zbar, out, stream);
+}
+
+#if D2D_TU_MODE == D2D_MODE_HARD
 int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, const float* Zbar, const BwdOut& out,
                      cudaStream_t stream, long long* launches) {
     if (method != D2D_METHOD_IMAGE) return (int)cudaErrorNotSupported;
@@ -457,25 +480,16 @@ int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, cons
     if (out.fixed_bar && (e = cudaMemsetAsync(out.fixed_bar, 0, sizeof(float) * 2 * p.T, stream)) != cudaSuccess) return (int)e;
     if (out.alpha_bar && (e = cudaMemsetAsync(out.alpha_bar, 0, sizeof(float), stream)) != cudaSuccess) return (int)e;
     if (p.R <= 0) return 0;
-    const bool txg = grid_role == D2D_GRID_TRANSMITTERS;
     int rc;
     switch (mode) {
-        case D2D_MODE_HARD:
-            rc = txg ? launch_bwd_one<D2D_MODE_HARD, true>(p, Zbar, out, stream)
-                     : launch_bwd_one<D2D_MODE_HARD, false>(p, Zbar, out, stream);
-            break;
-        case D2D_MODE_HARD_SIGMOID:
-            rc = txg ? launch_bwd_one<D2D_MODE_HARD_SIGMOID, true>(p, Zbar, out, stream)
-                     : launch_bwd_one<D2D_MODE_HARD_SIGMOID, false>(p, Zbar, out, stream);
-            break;
-        case D2D_MODE_SIGMOID:
-            rc = txg ? launch_bwd_one<D2D_MODE_SIGMOID, true>(p, Zbar, out, stream)
-                     : launch_bwd_one<D2D_MODE_SIGMOID, false>(p, Zbar, out, stream);
-            break;
+        case D2D_MODE_HARD: rc = launch_bwd_mode<D2D_MODE_HARD>(p, grid_role, method, Zbar, out, stream); break;
+        case D2D_MODE_HARD_SIGMOID: rc = launch_bwd_mode<D2D_MODE_HARD_SIGMOID>(p, grid_role, method, Zbar, out, stream); break;
+        case D2D_MODE_SIGMOID: rc = launch_bwd_mode<D2D_MODE_SIGMOID>(p, grid_role, method, Zbar, out, stream); break;
         default: return (int)cudaErrorInvalidValue;
     }
     if (launches) *launches += 1;
     return rc;
 }
+#endif
 
 }  // namespace d2d

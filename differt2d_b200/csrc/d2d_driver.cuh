@@ -99,47 +99,142 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     return t;
 }
 
-// Conservative tile test for an ImagePath candidate on a receivers grid.  `apex` is the last image of
-// the transmitter; the last interaction point of a receiver q is X = q + (vn/un) u (geometry.py:1093-1107)
-// and must satisfy min(s, 1 - s) > xz with s its parametric coordinate on the last object (geometry.py:
-// 595-621), xz = x_zero<MODE>.  Returns false only if NO point of the box can satisfy it.
-__device__ __forceinline__ bool tile_may_reach(const float2 apex, const float4 w0, const float4 w1, const int kind,
-                                               const float4 bbox, const float scale, const float xz, const float p_tolscale) {
-    if (kind == D2D_KIND_VERTEX) return true;
+// Conservative tile test for an ImagePath candidate on a receivers grid: returns false only if the validity
+// is EXACTLY 0 for every grid point of the tile, so that skipping the candidate changes nothing, bit for bit.
+//
+// The per-thread (canonical fp32) evaluation walks the interactions from the last to the first
+// (geometry.py:1093-1107): from the current point p (the receiver, then the previous interaction point) and
+// the apex A = I_{i+1} (image of the transmitter; computed here with the same `mirror`, hence bit-identical)
+//     u = p - A, v = P1 - p, g = (v.n)/(u.n), X = p + g u, s = t.(X - P1)/tt            (geometry.py:589-598)
+// and the path is dead (a_on == 0) unless min(s, 1 - s) > xz for every interaction.  s is a linear-fractional
+// function of p, so over a convex set of p on which u.n keeps its sign its extrema are at the extreme points:
+// the 4 corners of the tile's box for the last interaction, then the 2 end points of the reachable part of
+// the wall for the earlier ones.  Three exact rules are applied:
+//   (1) s-range: [smin, smax] misses [xz, 1 - xz] by more than the error bound `tol`;
+//   (2) wrong side: for walls, the residual of a specular interaction is e = (sign(-g_i) - sign(-g_{i-1})
+//       sign(1 + g_i)) u_hat (geometry.py:641-650), i.e. all residuals vanish iff every g_i lies in (-1, 0), and
+//       otherwise one of them is |e|^2 = 4: when some g-range is entirely outside [-1, 0] and every segment is
+//       long enough (>= Lmin) for the directions to be accurate, loss >= 3.9 > tol - xz and the path is dead;
+//   (3) zero-length walls (polygon closure walls of from_geojson, scene.py:646-652): n = 0, X = p, the
+//       residual is |i_hat|^2 = 1 unless the previous point coincides bit for bit: dead when that segment is
+//       provably longer than Lmin.
+// Error bound of s (first order, eps = 2^-24, S = largest coordinate magnitude in play).  Differences of
+// fp32 inputs carry RELATIVE errors (u, v exact up to eps|u|, eps|v|), the only absolute term is the final
+// rounding of X onto the fp32 lattice, eps (S + |g||u|):
+//     dX_c <= eps [S + |g||u| + 4|g||u_c| + 4.4 (|u_c|/|un|)(|v|_1 + |g||u|_1)] + L dev
+//     ds   <= (|t_x| dX_x + |t_y| dX_y)/tt + 4 eps |s|
+// with L = (1 + |g|)(1 + |u|/|un|) the Lipschitz constant of p -> X and dev the distance of the thread's
+// computed p from the convex set used here.  tol = 2.5 ds + 1e-6 covers both the threads' evaluation and the
+// (FMA-contracted) evaluation at the extreme points.
+template <int K>
+__device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (&c)[K > 0 ? K : 1],
+                                                  const float2 (&I)[K + 1], const float4 bbox, const float scale,
+                                                  const float xz, const float loss_dead /* tol_loss - xz */) {
     if (!(xz > -CUDART_INF_F)) return true;
-    const float qx[4] = {bbox.x, bbox.z, bbox.x, bbox.z};
-    const float qy[4] = {bbox.y, bbox.y, bbox.w, bbox.w};
-    float smin = CUDART_INF_F, smax = -CUDART_INF_F, unmin = CUDART_INF_F, gmax = 0.f, umax = 0.f, Gmax = 0.f;
-    int pos = 0, neg = 0;
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-        const float ux = qx[c] - apex.x, uy = qy[c] - apex.y;
-        const float vx = w0.x - qx[c], vy = w0.y - qy[c];
-        const float un = fmaf(ux, w1.x, uy * w1.y);
-        const float vn = fmaf(vx, w1.x, vy * w1.y);
-        pos += un > 0.f;
-        neg += un < 0.f;
-        const float g = vn / un;
-        const float Xx = fmaf(g, ux, qx[c]), Xy = fmaf(g, uy, qy[c]);
-        const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) / w1.z;
-        smin = fminf(smin, s);
-        smax = fmaxf(smax, s);
-        const float ul = sqrtf(fmaf(ux, ux, uy * uy));
-        unmin = fminf(unmin, fabsf(un));
-        gmax = fmaxf(gmax, fabsf(g));
-        umax = fmaxf(umax, ul);
-        Gmax = fmaxf(Gmax, fabsf(g) * ul);
-    }
-    if (!(pos == 4 || neg == 4)) return true;   // the denominator may vanish inside the box
-    if (!(smin == smin) || !(smax == smax)) return true;
-    // fp32 error of the exact evaluation, first order: the image carries ~2K eps S, so
-    // err(X) <~ 4 eps S (|g| + |u|/|un| + |g||u|/|un|) + eps S; 16 eps S (...) is used, times p_tolscale (4)
     const float eps = 5.9604645e-8f;
-    const float tolX = 16.0f * eps * scale * (gmax + umax / unmin + Gmax / unmin) + 4.0f * eps * (scale + Gmax);
-    const float tol = 1e-4f + p_tolscale * tolX / sqrtf(w1.z);
-    if (!(tol < CUDART_INF_F)) return true;
-    const float lo = xz - tol, hi = 1.0f - xz + tol;
-    return !(smax < lo || smin > hi);
+    const float S = scale;
+    const float Lmin = fmaxf(4096.0f * eps * S, 1e-15f);
+    float2 pts[4] = {make_float2(bbox.x, bbox.y), make_float2(bbox.z, bbox.y), make_float2(bbox.x, bbox.w),
+                     make_float2(bbox.z, bbox.w)};
+    int npts = 4;
+    float dev = 0.0f;
+    bool all_walls = true, any_deg = false;
+    bool g_out = false, lens_ok = true;
+    bool deg_pending = false, deg_dead = false;
+#pragma unroll
+    for (int i = K - 1; i >= 0; --i) {
+        const int j = c[i];
+        const float4 w0 = T.w0[j];
+        const float4 w1 = T.w1[j];
+        const int kind = T.kind[j];
+        if (kind != D2D_KIND_WALL) all_walls = false;
+        if (kind == D2D_KIND_VERTEX) continue;  // X = p, always on the object (geometry.py:387-403)
+        if (w0.z == 0.0f && w0.w == 0.0f) {      // zero-length object: n = 0, un == 0, X = p, s = 0
+            any_deg = true;
+            deg_pending = true;
+            // s = 0 passes on_objects iff act(0) != 0, i.e. xz < 0 (hard: 0 >= 0 is true)
+            continue;
+        }
+        const float2 A = I[i + 1];
+        float smin = CUDART_INF_F, smax = -CUDART_INF_F, gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
+        float unmin = CUDART_INF_F, U1 = 0.f, V1 = 0.f, uxm = 0.f, uym = 0.f, u2m = 0.f;
+        int pos = 0, neg = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q >= npts) break;
+            const float ux = pts[q].x - A.x, uy = pts[q].y - A.y;
+            const float vx = w0.x - pts[q].x, vy = w0.y - pts[q].y;
+            const float un = fmaf(ux, w1.x, uy * w1.y);
+            const float vn = fmaf(vx, w1.x, vy * w1.y);
+            pos += un > 0.f;
+            neg += un < 0.f;
+            const float g = vn / un;
+            const float Xx = fmaf(g, ux, pts[q].x), Xy = fmaf(g, uy, pts[q].y);
+            const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) / w1.z;
+            smin = fminf(smin, s); smax = fmaxf(smax, s);
+            gmin = fminf(gmin, g); gmax = fmaxf(gmax, g);
+            unmin = fminf(unmin, fabsf(un));
+            U1 = fmaxf(U1, fabsf(ux) + fabsf(uy));
+            V1 = fmaxf(V1, fabsf(vx) + fabsf(vy));
+            uxm = fmaxf(uxm, fabsf(ux)); uym = fmaxf(uym, fabsf(uy));
+            u2m = fmaxf(u2m, sqrtf(fmaf(ux, ux, uy * uy)));
+        }
+        if (!(pos == npts || neg == npts)) return true;            // u.n may vanish inside the set
+        if (!(smin == smin) || !(smax == smax) || !(gmin == gmin) || !(gmax == gmax)) return true;
+        if (!(unmin > 64.0f * eps * U1 + 4.0f * dev)) return true;  // u.n not reliably away from zero
+        const float gabs = fmaxf(fabsf(gmin), fabsf(gmax));
+        const float lip = (1.0f + gabs) * (1.0f + u2m / unmin);
+        const float amp = 4.4f * (V1 + gabs * U1) / unmin;
+        const float xmag = S + gabs * u2m;
+        const float dXx = eps * (xmag + 4.0f * gabs * uxm + amp * uxm) + 1.5f * lip * dev;
+        const float dXy = eps * (xmag + 4.0f * gabs * uym + amp * uym) + 1.5f * lip * dev;
+        const float smag = fmaxf(fabsf(smin), fabsf(smax));
+        const float ds = (fabsf(w0.z) * dXx + fabsf(w0.w) * dXy) / w1.z + 4.0f * eps * smag;
+        const float tol = 2.5f * ds + 1e-6f;
+        if (!(tol < CUDART_INF_F)) return true;
+        const float lo = xz - tol, hi = 1.0f - xz + tol;
+        if (smax < lo || smin > hi) return false;                  // rule (1)
+        // g-range and segment lengths for rules (2) and (3)
+        const float dg = 1.5f * dev * (1.0f + gabs) / unmin + 8.0f * eps * (gabs + (V1 + gabs * U1) / unmin);
+        const float glo = gmin - dg, ghi = gmax + dg;
+        if (ghi < -1.0f || glo > 0.0f) g_out = true;
+        const float g_abs_min = glo > 0.0f ? glo : (ghi < 0.0f ? -ghi : 0.0f);
+        const float g1_abs_min = (1.0f + glo) > 0.0f ? (1.0f + glo) : ((1.0f + ghi) < 0.0f ? -(1.0f + ghi) : 0.0f);
+        const float un_eff = unmin - 1.5f * dev - 8.0f * eps * U1;
+        const float seg_pb = g_abs_min * un_eff;    // |p - X| >= |g| |u.n|
+        const float seg_bA = g1_abs_min * un_eff;   // |X - A| >= |1 + g| |u.n|
+        if (!(seg_pb >= Lmin && seg_bA >= Lmin)) lens_ok = false;
+        if (deg_pending) {  // the zero-length object(s) between p and this X: previous point is X, distance |p - X|
+            if (seg_pb >= Lmin) deg_dead = true;
+            deg_pending = false;
+        }
+        // the reachable part of this object becomes the point set of the next (earlier) interaction
+        const float a = fmaxf(smin - tol, lo), b = fminf(smax + tol, hi);
+        pts[0] = make_float2(fmaf(a, w0.z, w0.x), fmaf(a, w0.w, w0.y));
+        pts[1] = make_float2(fmaf(b, w0.z, w0.x), fmaf(b, w0.w, w0.y));
+        npts = 2;
+        dev = 1.25f * fmaxf(dXx, dXy) + 2.0f * eps * S;
+    }
+    if (deg_pending) {  // zero-length object(s) right after the transmitter: previous point is tx = I[0]
+        float xl = CUDART_INF_F, xh = -CUDART_INF_F, yl = CUDART_INF_F, yh = -CUDART_INF_F;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            if (q >= npts) break;
+            xl = fminf(xl, pts[q].x); xh = fmaxf(xh, pts[q].x);
+            yl = fminf(yl, pts[q].y); yh = fmaxf(yh, pts[q].y);
+        }
+        const float dx = fmaxf(fmaxf(xl - I[0].x, I[0].x - xh), 0.0f);
+        const float dy = fmaxf(fmaxf(yl - I[0].y, I[0].y - yh), 0.0f);
+        if (fmaxf(dx, dy) - dev >= Lmin) deg_dead = true;
+    }
+    if (all_walls) {
+        if (any_deg) {
+            if (deg_dead && 0.98f >= loss_dead) return false;       // rule (3)
+        } else if (g_out && lens_ok && 3.9f >= loss_dead) {
+            return false;                                           // rule (2)
+        }
+    }
+    return true;
 }
 
 // number of candidates of order K over m visitable objects
@@ -197,11 +292,11 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
             }
             keep = true;
             if (cull) {
-                float2 I = fx;
+                float2 I[K + 1];
+                I[0] = fx;
 #pragma unroll
-                for (int i = 0; i < K; ++i) I = mirror(I, T.w0[c[i]], T.w1[c[i]]);
-                const int j = c[K - 1];
-                keep = tile_may_reach(I, T.w0[j], T.w1[j], T.kind[j], tile.bbox, tile.scale, xz, (float)p.cull);
+                for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[c[i]], T.w1[c[i]]);
+                keep = tile_may_be_valid<K>(T, c, I, tile.bbox, tile.scale, xz, p.tol - xz);
             }
         }
         // ordered compaction: per-warp segments keep list order

@@ -77,8 +77,6 @@ static long long host_tile_blocks(const KParams& p) {
     return (p.R + kBlock - 1) / kBlock;
 }
 
-long long num_tile_blocks(const KParams& p) { return host_tile_blocks(p); }
-
 template <int MODE, int METHOD, bool TXGRID>
 static int launch_one(const KParams& p, float* Z, float* valid_out, cudaStream_t stream) {
     const long long nblk = host_tile_blocks(p);
@@ -109,6 +107,19 @@ static int launch_method(const KParams& p, int grid_role, int method, float* Z, 
     return (int)cudaErrorInvalidValue;
 }
 
+#ifndef D2D_TU_MODE
+#error "compile with -DD2D_TU_MODE=<D2D_MODE_*> (differt2d_b200/build.py)"
+#endif
+
+template <>
+int launch_fwd_mode<D2D_TU_MODE>(const KParams& p, int grid_role, int method, float* Z, float* valid_out,
+                                 cudaStream_t s) {
+    return launch_method<D2D_TU_MODE>(p, grid_role, method, Z, valid_out, s);
+}
+
+#if D2D_TU_MODE == D2D_MODE_HARD
+long long num_tile_blocks(const KParams& p) { return host_tile_blocks(p); }
+
 int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, float* Z, float* valid_out,
                      cudaStream_t stream, long long* launches) {
     if (p.R <= 0) return 0;
@@ -118,15 +129,16 @@ int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, floa
     }
     int e;
     switch (mode) {
-        case D2D_MODE_HARD: e = launch_method<D2D_MODE_HARD>(p, grid_role, method, Z, valid_out, stream); break;
+        case D2D_MODE_HARD: e = launch_fwd_mode<D2D_MODE_HARD>(p, grid_role, method, Z, valid_out, stream); break;
         case D2D_MODE_HARD_SIGMOID:
-            e = launch_method<D2D_MODE_HARD_SIGMOID>(p, grid_role, method, Z, valid_out, stream);
+            e = launch_fwd_mode<D2D_MODE_HARD_SIGMOID>(p, grid_role, method, Z, valid_out, stream);
             break;
-        case D2D_MODE_SIGMOID: e = launch_method<D2D_MODE_SIGMOID>(p, grid_role, method, Z, valid_out, stream); break;
+        case D2D_MODE_SIGMOID: e = launch_fwd_mode<D2D_MODE_SIGMOID>(p, grid_role, method, Z, valid_out, stream); break;
         default: return (int)cudaErrorInvalidValue;
     }
     if (launches) *launches += 1;
     return e;
 }
+#endif
 
 }  // namespace d2d

@@ -23,4 +23,16 @@ int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, floa
 int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, const float* Zbar, const BwdOut& out,
                      cudaStream_t stream, long long* launches);
 
+// One translation unit per logic mode (compiled from the same source with -DD2D_TU_MODE=<mode>, in parallel).
+template <int MODE>
+int launch_fwd_mode(const KParams& p, int grid_role, int method, float* Z, float* valid_out, cudaStream_t s);
+template <int MODE>
+int launch_bwd_mode(const KParams& p, int grid_role, int method, const float* Zbar, const BwdOut& out, cudaStream_t s);
+template <> int launch_fwd_mode<D2D_MODE_HARD>(const KParams&, int, int, float*, float*, cudaStream_t);
+template <> int launch_fwd_mode<D2D_MODE_HARD_SIGMOID>(const KParams&, int, int, float*, float*, cudaStream_t);
+template <> int launch_fwd_mode<D2D_MODE_SIGMOID>(const KParams&, int, int, float*, float*, cudaStream_t);
+template <> int launch_bwd_mode<D2D_MODE_HARD>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
+template <> int launch_bwd_mode<D2D_MODE_HARD_SIGMOID>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
+template <> int launch_bwd_mode<D2D_MODE_SIGMOID>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
+
 }  // namespace d2d
