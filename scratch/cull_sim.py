@@ -40,7 +40,8 @@ def spar(Xp, j):
 cands = [(a,) for a in range(N)] + [(a, b) for a in range(N) for b in range(N) if a != b]
 ntx, nty = 1024 // TW, 1024 // TH
 tiles = [(rng.integers(ntx), rng.integers(nty)) for _ in range(200)]
-tot = 0; surv1 = 0; surv1tight = 0; surv2 = 0; pt_on_last = 0; pt_on_all = 0; npts = 0
+deg = (np.abs(t).sum(-1) == 0)
+tot = 0; pt_spec = 0; surv3 = 0; surv1 = 0; surv1tight = 0; surv2 = 0; pt_on_last = 0; pt_on_all = 0; npts = 0
 for (bx, by) in tiles:
     xs = X[0, bx * TW:(bx + 1) * TW]; ys = Y[by * TH:(by + 1) * TH, 0]
     box = np.array([[xs.min(), ys.min()], [xs.max(), ys.min()], [xs.min(), ys.max()], [xs.max(), ys.max()]])
@@ -61,6 +62,14 @@ for (bx, by) in tiles:
             X1, _, _ = backproj(Xp, Is[1], c[0])
             s1 = spar(X1, c[0])
             on_all &= np.minimum(s1, 1 - s1) > xz
+        # specular: g in (-1,0) at every interaction (per point)
+        _, unl, gl = backproj(pts, Is[-1], j)
+        spec = (gl > -1) & (gl < 0)
+        if len(c) == 2:
+            _, _, g0 = backproj(Xp, Is[1], c[0])
+            spec &= (g0 > -1) & (g0 < 0)
+        anydeg = any(deg[k] for k in c)
+        pt_spec += (on_all & spec & (not anydeg)).sum()
         pt_on_last += on_last.sum(); pt_on_all += on_all.sum(); npts += len(pts)
         # stage 1 at corners
         Xc, unc, gc = backproj(box, Is[-1], j)
@@ -98,5 +107,6 @@ for (bx, by) in tiles:
         tol1 = 2.5 * E1 + 1e-6
         keep2 = not (s1e.max() < xz - tol1 or s1e.min() > 1 - xz + tol1)
         surv2 += keep2
+print(f"per-point on_all & specular & non-degenerate: {pt_spec/npts:.4f}")
 print(f"{coords} tiles {TW}x{TH}: candidates/tile {len(cands)}; survive old stage1 {surv1/tot:.4f}; tight stage1 {surv1tight/tot:.4f}; "
       f"tight stage1+2 {surv2/tot:.4f}; per-point on_last {pt_on_last/npts:.4f} on_all {pt_on_all/npts:.4f}")
