@@ -58,6 +58,7 @@ class D2DProblem(C.Structure):
         ("reduce_all", C.c_int32),
         ("grad_mode", C.c_int32),
         ("no_cull", C.c_int32),
+        ("candidate_slices", C.c_int32),
     ]
 
 

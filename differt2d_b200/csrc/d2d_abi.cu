@@ -161,6 +161,24 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
         total += c;
     }
     k.C_total = total;
+    // Launch geometry.  Links with very few grid points (point-to-point, scene.py:1272-1334) get one point per
+    // CTA (the tile cull is then exact up to rounding) and share their candidate list among `slices` CTAs.
+    k.tile_points = 128;
+    k.slices = 1;
+    if (k.grid_cols == 0 && p->n_grid <= 32 && total >= 4096) k.tile_points = 1;
+    if (p->candidate_slices > 0) {
+        k.slices = p->candidate_slices;
+    } else if (total >= 16384) {
+        long long nblk = k.grid_cols > 0 ? ((k.grid_cols + 15) / 16) * ((p->n_grid / k.grid_cols + 7) / 8)
+                                         : (p->n_grid + k.tile_points - 1) / k.tile_points;
+        if (nblk < 1) nblk = 1;
+        long long want = (148LL * 8) / nblk;                      // fill the machine about 8 CTAs deep
+        const long long chunks = (total + 127) / 128;
+        if (want > chunks / 4) want = chunks / 4;                  // at least 4 chunks per CTA
+        if (want > 65535) want = 65535;
+        if (want > 1) k.slices = (int)want;
+    }
+    if (k.slices > 65535) return fail(D2D_ERR_INVALID_ARGUMENT, "candidate_slices must be <= 65535");
     return D2D_OK;
 }
 

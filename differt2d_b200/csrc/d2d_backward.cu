@@ -390,9 +390,15 @@ __global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, cons
             if (p.reduce_all) {
                 zsum = zsum + A.acc;
                 gsum.x += A.grid_bar.x; gsum.y += A.grid_bar.y;
-            } else {
+            } else if (gridDim.y == 1) {
                 if (out.Z) out.Z[(long long)t * p.R + r] = A.acc;
                 if (out.grid_bar) reinterpret_cast<float2*>(out.grid_bar)[(long long)t * p.R + r] = A.grid_bar;
+            } else {  // candidate slices: outputs zeroed by the launcher
+                if (out.Z && A.acc != 0.f) atomicAdd(&out.Z[(long long)t * p.R + r], A.acc);
+                if (out.grid_bar) {
+                    if (A.grid_bar.x != 0.f) atomicAdd(&out.grid_bar[2 * ((long long)t * p.R + r) + 0], A.grid_bar.x);
+                    if (A.grid_bar.y != 0.f) atomicAdd(&out.grid_bar[2 * ((long long)t * p.R + r) + 1], A.grid_bar.y);
+                }
             }
         }
         alpha_total += A.alpha_bar;
@@ -410,8 +416,16 @@ __global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, cons
         }
     }
     if (active && p.reduce_all) {
-        if (out.Z) out.Z[r] = zsum;
-        if (out.grid_bar) reinterpret_cast<float2*>(out.grid_bar)[r] = gsum;
+        if (gridDim.y == 1) {
+            if (out.Z) out.Z[r] = zsum;
+            if (out.grid_bar) reinterpret_cast<float2*>(out.grid_bar)[r] = gsum;
+        } else {
+            if (out.Z && zsum != 0.f) atomicAdd(&out.Z[r], zsum);
+            if (out.grid_bar) {
+                if (gsum.x != 0.f) atomicAdd(&out.grid_bar[2 * r + 0], gsum.x);
+                if (gsum.y != 0.f) atomicAdd(&out.grid_bar[2 * r + 1], gsum.y);
+            }
+        }
     }
     if (out.alpha_bar) {
         const float as = warp_sum(alpha_total);
@@ -433,12 +447,10 @@ __global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, cons
     }
 }
 
-static long long bwd_tile_blocks(const KParams& p);
-
 template <int MODE, bool TXGRID>
 static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out, cudaStream_t stream) {
     const int block = kBlock;
-    const long long nblk = bwd_tile_blocks(p);
+    const long long nblk = host_tile_blocks(p);
     size_t smem = ((scene_tab_bytes(p.N) + 15) / 16) * 16;
     if (out.objects_bar || out.phis_bar) smem += (size_t)5 * p.N * sizeof(float);
     auto kern = power_bwd_kernel<MODE, TXGRID>;
@@ -446,21 +458,13 @@ static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<(unsigned)nblk, block, smem, stream>>>(p, Zbar, out);
+    kern<<<dim3((unsigned)nblk, (unsigned)p.slices), block, smem, stream>>>(p, Zbar, out);
     return (int)cudaGetLastError();
 }
 
 #ifndef D2D_TU_MODE
 #error "compile with -DD2D_TU_MODE=<D2D_MODE_*> (differt2d_b200/build.py)"
 #endif
-
-static long long bwd_tile_blocks(const KParams& p) {
-    if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
-        const long long rows = p.R / p.grid_cols;
-        return (long long)((p.grid_cols + kTileCols - 1) / kTileCols) * ((rows + kTileRows - 1) / kTileRows);
-    }
-    return (p.R + kBlock - 1) / kBlock;
-}
 
 template <>
 int launch_bwd_mode<D2D_TU_MODE>(const KParams& p, int grid_role, int method, const float* Zbar, const BwdOut& out,
@@ -480,6 +484,11 @@ int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, cons
     if (out.fixed_bar && (e = cudaMemsetAsync(out.fixed_bar, 0, sizeof(float) * 2 * p.T, stream)) != cudaSuccess) return (int)e;
     if (out.alpha_bar && (e = cudaMemsetAsync(out.alpha_bar, 0, sizeof(float), stream)) != cudaSuccess) return (int)e;
     if (p.R <= 0) return 0;
+    if (p.slices > 1) {
+        const size_t nz = (size_t)(p.reduce_all ? 1 : p.T) * p.R;
+        if (out.Z && (e = cudaMemsetAsync(out.Z, 0, sizeof(float) * nz, stream)) != cudaSuccess) return (int)e;
+        if (out.grid_bar && (e = cudaMemsetAsync(out.grid_bar, 0, sizeof(float) * 2 * nz, stream)) != cudaSuccess) return (int)e;
+    }
     int rc;
     switch (mode) {
         case D2D_MODE_HARD: rc = launch_bwd_mode<D2D_MODE_HARD>(p, grid_role, method, Zbar, out, stream); break;

@@ -47,6 +47,8 @@ struct KParams {
     long long R;
     int grid_cols;         // row length of the grid when it is a row-major n x m mesh (0: unknown)
     int cull;              // tile-level candidate culling on/off (results are identical either way)
+    int slices;            // gridDim.y: CTAs sharing one tile, each walking every slices-th chunk of candidates
+    int tile_points;       // grid points per CTA when the tile is 1-D (<= kBlock; 1 for point-to-point links)
     int N, T;
     int min_order, max_order;
     int steps;

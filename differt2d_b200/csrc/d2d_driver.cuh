@@ -39,12 +39,13 @@ struct DriverShared {
     int4 list[2][kBlock];    // packed survivors: (c0 | c1 << 16, c2 | c3 << 16, index lo, index hi)
 };
 
-__device__ __forceinline__ long long tile_grid_blocks(const long long R, const int cols) {
-    if (cols > 0 && R % cols == 0) {
-        const long long rows = R / cols;
-        return ((cols + kTileCols - 1) / kTileCols) * ((rows + kTileRows - 1) / kTileRows);
+// CTAs along x for a problem (host side)
+inline long long host_tile_blocks(const KParams& p) {
+    if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
+        const long long rows = p.R / p.grid_cols;
+        return (long long)((p.grid_cols + kTileCols - 1) / kTileCols) * ((rows + kTileRows - 1) / kTileRows);
     }
-    return (R + kBlock - 1) / kBlock;
+    return (p.R + p.tile_points - 1) / p.tile_points;
 }
 
 // Maps (blockIdx, threadIdx) to a grid point; computes the tile's bounding box (all threads must call).
@@ -61,8 +62,8 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
         t.active = col < p.grid_cols && row < rows;
         t.r = row * p.grid_cols + col;
     } else {
-        t.r = (long long)blockIdx.x * kBlock + tid;
-        t.active = t.r < p.R;
+        t.r = (long long)blockIdx.x * p.tile_points + tid;
+        t.active = tid < p.tile_points && t.r < p.R;
     }
     float xmin = CUDART_INF_F, ymin = CUDART_INF_F, xmax = -CUDART_INF_F, ymax = -CUDART_INF_F;
     if (t.active) {
@@ -259,14 +260,15 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     if constexpr (K == 0) {
         Cand<0> cd;
         cd.c[0] = 0;
-        visit(cd, col0);
+        if (blockIdx.y == 0) visit(cd, col0);  // uniform over the CTA
         return;
     }
     constexpr int KK = K > 0 ? K : 1;
     const bool cull = (METHOD == D2D_METHOD_IMAGE) && !TXGRID && p.cull;
     const float xz = x_zero<MODE>(alpha);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    for (long long base = 0; base < Ck; base += kBlock) {
+    // candidate slices (point-to-point links with huge candidate lists): CTA y walks chunks y, y + slices, ...
+    for (long long base = (long long)blockIdx.y * kBlock; base < Ck; base += (long long)kBlock * gridDim.y) {
         const long long idx = base + tid;
         bool keep = false;
         int c[KK];

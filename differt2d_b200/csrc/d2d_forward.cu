@@ -63,18 +63,14 @@ __global__ void __launch_bounds__(kBlock) power_fwd_kernel(const KParams p, floa
         }
         if (tile.active) {
             if (p.reduce_all) zsum = zsum + acc;  // scene.py:1939-1952 (0.0 + p0 + p1 ...)
-            else Z[(long long)t * p.R + tile.r] = acc;
+            else if (gridDim.y == 1) Z[(long long)t * p.R + tile.r] = acc;
+            else if (acc != 0.0f) atomicAdd(&Z[(long long)t * p.R + tile.r], acc);  // Z zeroed by the launcher
         }
     }
-    if (tile.active && p.reduce_all) Z[tile.r] = zsum;
-}
-
-static long long host_tile_blocks(const KParams& p) {
-    if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
-        const long long rows = p.R / p.grid_cols;
-        return (long long)((p.grid_cols + kTileCols - 1) / kTileCols) * ((rows + kTileRows - 1) / kTileRows);
+    if (tile.active && p.reduce_all) {
+        if (gridDim.y == 1) Z[tile.r] = zsum;
+        else if (zsum != 0.0f) atomicAdd(&Z[tile.r], zsum);
     }
-    return (p.R + kBlock - 1) / kBlock;
 }
 
 template <int MODE, int METHOD, bool TXGRID>
@@ -86,7 +82,7 @@ static int launch_one(const KParams& p, float* Z, float* valid_out, cudaStream_t
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<(unsigned)nblk, kBlock, smem, stream>>>(p, Z, valid_out);
+    kern<<<dim3((unsigned)nblk, (unsigned)p.slices), kBlock, smem, stream>>>(p, Z, valid_out);
     return (int)cudaGetLastError();
 }
 
@@ -123,6 +119,10 @@ long long num_tile_blocks(const KParams& p) { return host_tile_blocks(p); }
 int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, float* Z, float* valid_out,
                      cudaStream_t stream, long long* launches) {
     if (p.R <= 0) return 0;
+    if (p.slices > 1) {  // partial sums of the candidate slices are combined with atomics
+        const cudaError_t e = cudaMemsetAsync(Z, 0, sizeof(float) * (size_t)(p.reduce_all ? 1 : p.T) * p.R, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
     if (valid_out) {
         const cudaError_t e = cudaMemsetAsync(valid_out, 0, sizeof(float) * (size_t)p.T * p.R * p.C_total, stream);
         if (e != cudaSuccess) return (int)e;

@@ -42,6 +42,7 @@ class TraceConfig:
     reduce_all: bool = False
     grid_cols: int = 0  # row length of a row-major mesh grid (enables 16 x 8 tiles); 0 = unknown
     cull: bool = True   # tile-level candidate culling (identical results)
+    candidate_slices: int = 0  # 0 = automatic; > 1 splits each tile's candidate list over that many CTAs
 
 
 def _dev_f32(x, device) -> torch.Tensor:
@@ -107,6 +108,7 @@ class _Packed:
         p.reduce_all = int(cfg.reduce_all)
         p.grid_cols = int(cfg.grid_cols)
         p.no_cull = 0 if cfg.cull else 1
+        p.candidate_slices = int(cfg.candidate_slices)
         self.p = p
         self.T = self.fixed.shape[0]
         self.R = self.grid.shape[0]

@@ -99,6 +99,9 @@ typedef struct D2DProblem {
     int32_t reduce_all; /* sum over the fixed points (scene.py:1939-1952)                          */
     int32_t grad_mode;  /* D2D_GRAD_*                                                              */
     int32_t no_cull;    /* 1 disables the tile-level candidate culling (identical results, slower)        */
+    int32_t candidate_slices; /* 0 = automatic.  > 1: that many CTAs share each tile's candidate list and combine  */
+                              /* their partial sums with fp32 atomics (point-to-point links with huge lists, e.g.  */
+                              /* 500 objects at order 3); the summation order of Z is then not the list order.     */
 } D2DProblem;
 
 /* Fills a problem with the reference's defaults (defaults.py, geometry.py:915, optimize.py:49,83). */

@@ -310,6 +310,60 @@ def test_cull_equals_nocull_mixed_objects():
         assert torch.equal(a, b), (mode, int((a != b).sum()))
 
 
+# ---- point-to-point links with long candidate lists (candidate slices) ------------------------------
+def _random_walls(n, seed=1234, length=None):
+    """random_uniform_scene analogue (scene.py:718-733: TX points first, then walls, RX last) with SHORT walls
+    (length ~ 1.5/n around uniform centres), so that some multi-bounce paths survive the occlusion test."""
+    rng = np.random.default_rng(seed)
+    length = (1.5 / n) if length is None else length
+    c = rng.random((n, 2), dtype=np.float32)
+    a = rng.random(n, dtype=np.float32) * np.float32(np.pi)
+    h = (0.5 * length * np.stack([np.cos(a), np.sin(a)], -1)).astype(np.float32)
+    walls = np.stack([c - h, c + h], 1)
+    pts = rng.random((5, 2), dtype=np.float32)
+    sc = d.Scene.from_walls_array(walls)
+    return sc.with_transmitters(tx_0=d.Point(xy=pts[0]), tx_1=d.Point(xy=pts[1])).with_receivers(
+        rx_0=d.Point(xy=pts[2]), rx_1=d.Point(xy=pts[3]), rx_2=d.Point(xy=pts[4]))
+
+
+@pytest.mark.parametrize("mode", ["hard", "hard_sigmoid"])
+def test_candidate_slices_equal_unsliced(mode):
+    """Splitting a tile's candidate list over several CTAs only changes the summation order of Z."""
+    sc = SCENES["geojson_norm"]
+    X, Y = H.jittered_grid(sc, 3, 2, seed=9)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    Za, va = F.power_fwd(_cfg(mode, max_order=2, candidate_slices=1), xys, fixed, grid, alpha=100.0, want_valid=True,
+                         device="cuda")
+    Zb, vb = F.power_fwd(_cfg(mode, max_order=2, candidate_slices=5), xys, fixed, grid, alpha=100.0, want_valid=True,
+                         device="cuda")
+    assert torch.equal(va, vb)
+    assert torch.allclose(Za, Zb, rtol=1e-6, atol=0)
+    ga = F.power_bwd(_cfg(mode, max_order=2, candidate_slices=1), xys, fixed, grid, None, alpha=100.0, device="cuda")
+    gb = F.power_bwd(_cfg(mode, max_order=2, candidate_slices=5), xys, fixed, grid, None, alpha=100.0, device="cuda")
+    for k in ga:
+        scale = max(ga[k].abs().max().item(), 1e-30)
+        assert torch.allclose(ga[k], gb[k], rtol=1e-4, atol=1e-5 * scale), k
+
+
+@pytest.mark.parametrize("n_walls,order", [(60, 3), (500, 2)])
+def test_point_to_point_long_lists_vs_oracle(n_walls, order):
+    """accumulate_over_paths-style links (2 TX x 3 RX) on random_uniform_scene analogues: 208 860 (60 walls,
+    order 3) and 249 500 (500 walls, order 2) candidates per link, automatic slicing, hard logic.
+    Validity is bit-exact per candidate; Z up to the summation order."""
+    sc = _random_walls(n_walls, length=0.15 if n_walls == 60 else None)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    grid = np.stack([p.xy for p in sc.receivers.values()])
+    cfg = _cfg("hard", min_order=order, max_order=order)
+    Z, v = F.power_fwd(cfg, xys, fixed, grid, want_valid=True, device="cuda")
+    Zo, vo = CO.power_map(xys, fixed, grid, min_order=order, max_order=order, mode="hard", want_valid=True)
+    assert np.array_equal(v.cpu().numpy(), vo)
+    np.testing.assert_allclose(Z.cpu().numpy(), Zo, rtol=1e-5, atol=1e-7)
+    assert vo.sum() > 0
+
+
 # ---- FermatPath / MinPath (in-register Adam solver) -----------------------------------------------
 def _vertex_scene():
     """examples/plot_vertex_diffraction_power_map.py:35-38,70-72 — basic_scene, wall 5 replaced by its
