@@ -15,3 +15,4 @@ k=l["roofline"]["kernels"]
 print("$c", "step %.3f ms  fwd %.3f  bwd %.3f  e2e %.3f ms" % (l["ms_per_step"], k["power_fwd_kernel"]["ms"], k["power_bwd_kernel"]["ms"], l["e2e"]["ms_per_step"]))
 PY
 done
+timeout 600 python scripts/bench_configs.py > $OUT/bench_configs.jsonl 2> $OUT/bench_configs.err; echo "configs rc=$?"; cut -c1-220 $OUT/bench_configs.jsonl
