@@ -25,6 +25,9 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-prec-div=tr
 # (source, object, extra flags): the kernel sources are compiled once per logic mode, in parallel
 UNITS = [("d2d_forward.cu", f"d2d_forward_m{m}.o", ["-fmad=false", f"-DD2D_TU_MODE={m}"]) for m in (1, 0, 2)]
 UNITS += [("d2d_backward.cu", f"d2d_backward_m{m}.o", ["-fmad=false", f"-DD2D_TU_MODE={m}"]) for m in (1, 0, 2)]
+# reverse mode through the Adam scan of FermatPath / MinPath: the slowest units, listed first
+UNITS = [("d2d_backward.cu", f"d2d_backward_solver_m{m}.o", ["-fmad=false", f"-DD2D_TU_MODE={m}", "-DD2D_TU_SOLVER=1"])
+         for m in (1, 0, 2)] + UNITS
 UNITS += [("d2d_abi.cu", "d2d_abi.o", [])]
 
 

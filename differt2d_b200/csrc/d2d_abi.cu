@@ -291,8 +291,8 @@ int d2d_power_bwd(const D2DProblem* p, const float* Zbar, float* Z_out, float* g
     d2d::KParams k;
     const int rc = pack(p, k);
     if (rc != D2D_OK) return rc;
-    if (p->method != D2D_METHOD_IMAGE)
-        return fail(D2D_ERR_UNSUPPORTED, "reverse mode is implemented for ImagePath only (Fermat/MinPath: forward)");
+    if (p->method != D2D_METHOD_IMAGE && !p->x0 && p->max_order > 0)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "Fermat/MinPath need x0 (initial guesses per candidate)");
     d2d::BwdOut out{Z_out, grid_bar, objects_bar, phis_bar, fixed_bar, alpha_bar};
     long long n = 0;
     const int e = d2d::launch_power_bwd(k, p->mode, p->grid_role, p->method, Zbar, out, (cudaStream_t)stream, &n);

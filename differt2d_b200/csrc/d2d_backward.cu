@@ -13,6 +13,7 @@
 #include "d2d_driver.cuh"
 #include "d2d_launch.h"
 #include "d2d_solver.cuh"
+#include "d2d_solver_adj.cuh"
 
 namespace d2d {
 
@@ -22,14 +23,16 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
-// Reverse sweep of one ImagePath.  Returns valid * fun; when the path carries gradient, `has` is set
-// and tx_bar / rx_bar / alpha_bar / oa[] / occ_* are filled (not accumulated).
-template <int MODE, int K>
-__device__ __noinline__ float path_vjp_image(const SceneTab& T, const KParams& p, const float alpha,
-                                                const Cand<K>& cd, const float2 tx, const float2 rx,
-                                                const float zbar, bool& has, float2& tx_bar, float2& rx_bar,
-                                                float& alpha_bar, ObjAdj (&oa)[K > 0 ? K : 1], int& occ_j,
-                                                float4& occ_bar) {
+// Reverse sweep of one path (ImagePath: closed form; FermatPath / MinPath: through the Adam scan, see
+// d2d_solver_adj.cuh).  Returns valid * fun; when the path carries gradient, `has` is set and tx_bar / rx_bar /
+// alpha_bar / oa[] / occ_* are filled (not accumulated).
+template <int MODE, int METHOD, int K>
+__device__ __noinline__ float path_vjp(const SceneTab& T, const KParams& p, const float alpha,
+                                          const Cand<K>& cd, const float2 tx, const float2 rx, const long long col,
+                                          const float zbar, bool& has, float2& tx_bar, float2& rx_bar,
+                                          float& alpha_bar, ObjAdj (&oa)[K > 0 ? K : 1], int& occ_j,
+                                          float4& occ_bar) {
+    constexpr bool kSolver = (METHOD != D2D_METHOD_IMAGE) && K > 0;
     has = false;
     occ_j = -1;
     // ---- recompute the forward, keeping what the reverse sweep needs --------------------------
@@ -38,9 +41,16 @@ __device__ __noinline__ float path_vjp_image(const SceneTab& T, const KParams& p
     X[0] = tx;
     X[K + 1] = rx;
     I[0] = tx;
+    AdamState<K> ck[kSolver ? kNck : 1];
+    AdamState<K> th_final;
+    float solver_loss = 0.f;
+    const int stride = adam_ckpt_stride(p.steps);
+    if constexpr (kSolver) {
+        solver_loss = adam_scan_ckpt<METHOD, K>(T, p, cd, tx, rx, col, stride, ck, th_final);
+        place_points<K>(T, cd, th_final.th, X);
+    } else {
 #pragma unroll
-    for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[cd.c[i]], T.w1[cd.c[i]]);
-    {
+        for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[cd.c[i]], T.w1[cd.c[i]]);
         float2 q = rx;
 #pragma unroll
         for (int i = K - 1; i >= 0; --i) {
@@ -67,7 +77,8 @@ __device__ __noinline__ float path_vjp_image(const SceneTab& T, const KParams& p
         a_on = act<MODE>(onx, alpha);
         if (a_on == 0.0f) return 0.0f;
     }
-    const float loss = path_loss<K>(T, cd, X);
+    // FermatPath's loss is path_loss(xys) (geometry.py:1202-1204), MinPath's is the scan's last loss (:1286-1288)
+    const float loss = (kSolver && METHOD == D2D_METHOD_MINPATH) ? solver_loss : path_loss<K>(T, cd, X);
     const float lx = p.tol - loss;
     float a_l = 1.0f;
     if (MODE == D2D_MODE_HARD) {
@@ -100,6 +111,7 @@ __device__ __noinline__ float path_vjp_image(const SceneTab& T, const KParams& p
 #pragma unroll
     for (int i = 0; i < K; ++i) oa[i].zero();
     alpha_bar = 0.f;
+    float solver_loss_bar = 0.f;
 
     // (1) fun(path) : utils.py:52-54 / length**2 ; path_length geometry.py:199-203
     {
@@ -154,7 +166,9 @@ __device__ __noinline__ float path_vjp_image(const SceneTab& T, const KParams& p
             const float dz = act_dz<MODE>(lx, alpha);
             const float loss_bar = -share * alpha * dz;
             alpha_bar += share * lx * dz;
-            if (loss_bar != 0.f) {
+            if (kSolver && METHOD == D2D_METHOD_MINPATH) {
+                solver_loss_bar = loss_bar;  // flows into loss_fun(theta_{S-1}), inside the scan
+            } else if (loss_bar != 0.f) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
                     const int j = cd.c[i];
@@ -217,6 +231,26 @@ __device__ __noinline__ float path_vjp_image(const SceneTab& T, const KParams& p
         }
     }
 
+    if constexpr (kSolver) {
+        // (3') xys = parametric_to_cartesian(objects, theta_S) (geometry.py:1200, 1284), then the Adam scan
+        constexpr int KK = K > 0 ? K : 1;
+        float thb[KK];
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            const float4 w0 = T.w0[cd.c[i]];
+            oa[i].p1.x += Xb[i + 1].x; oa[i].p1.y += Xb[i + 1].y;
+            thb[i] = 0.f;
+            if (T.kind[cd.c[i]] != D2D_KIND_VERTEX) {
+                thb[i] = Xb[i + 1].x * w0.z + Xb[i + 1].y * w0.w;
+                oa[i].t.x += th_final.th[i] * Xb[i + 1].x;
+                oa[i].t.y += th_final.th[i] * Xb[i + 1].y;
+            }
+        }
+        tx_bar = Xb[0];
+        rx_bar = Xb[K + 1];
+        adam_scan_reverse<METHOD, K>(T, p, cd, tx, rx, stride, ck, thb, solver_loss_bar, tx_bar, rx_bar, oa);
+        return contrib;
+    }
     // (3) backward scan of the image method : geometry.py:1093-1107 (clean `where`)
     float2 Ib[K + 1];
 #pragma unroll
@@ -275,15 +309,15 @@ struct BwdAcc {
     float acc;
 };
 
-template <int MODE, int K, bool TXGRID>
+template <int MODE, int METHOD, int K, bool TXGRID>
 __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
                                               const float alpha, const float2 fx, const float2 g, const long long col0,
                                               int& buf, const float zbar, BwdAcc& A, float* s_obj, float* s_phi) {
     constexpr int KK = K > 0 ? K : 1;
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
-    for_each_candidate<MODE, D2D_METHOD_IMAGE, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long) {
+    for_each_candidate<MODE, METHOD, K, TXGRID>(
+        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col) {
             bool has = false;
             float2 txb = make_float2(0.f, 0.f), rxb = make_float2(0.f, 0.f);
             float ab = 0.f;
@@ -294,11 +328,13 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
                 // light re-trace first (same code as the forward kernel); the reverse sweep is out of line
                 // and only runs for the few paths whose validity is non-zero
                 float2 X[K + 2];
-                image_path<K>(T, cd, tx, rx, X);
-                const float valid = validity<MODE, K, true>(T, p, alpha, cd, X, 0.0f);
+                float loss;
+                construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
+                const float valid =
+                    validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
                 if (valid != 0.0f) {
-                    const float c = path_vjp_image<MODE, K>(T, p, alpha, cd, tx, rx, zbar, has, txb, rxb, ab, oa,
-                                                            occ_j, occ_bar);
+                    const float c = path_vjp<MODE, METHOD, K>(T, p, alpha, cd, tx, rx, col, zbar, has, txb, rxb, ab,
+                                                              oa, occ_j, occ_bar);
                     A.acc = A.acc + c;
                 }
             }
@@ -340,7 +376,7 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
         });
 }
 
-template <int MODE, bool TXGRID>
+template <int MODE, int METHOD, bool TXGRID>
 __global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, const float* __restrict__ Zbar,
                                                            const BwdOut out) {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -377,11 +413,11 @@ __global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, cons
         long long col0 = 0;
         for (int k = p.min_order; k <= p.max_order; ++k) {
             switch (k) {
-                case 0: run_order_bwd<MODE, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 1: run_order_bwd<MODE, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 2: run_order_bwd<MODE, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 3: run_order_bwd<MODE, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 4: run_order_bwd<MODE, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 0: run_order_bwd<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 1: run_order_bwd<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 2: run_order_bwd<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 3: run_order_bwd<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 4: run_order_bwd<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
                 default: break;
             }
             col0 += order_count(k, T.n_allowed);
@@ -447,13 +483,13 @@ __global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, cons
     }
 }
 
-template <int MODE, bool TXGRID>
+template <int MODE, int METHOD, bool TXGRID>
 static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out, cudaStream_t stream) {
     const int block = kBlock;
     const long long nblk = host_tile_blocks(p);
     size_t smem = ((scene_tab_bytes(p.N) + 15) / 16) * 16;
     if (out.objects_bar || out.phis_bar) smem += (size_t)5 * p.N * sizeof(float);
-    auto kern = power_bwd_kernel<MODE, TXGRID>;
+    auto kern = power_bwd_kernel<MODE, METHOD, TXGRID>;
     if (smem > 48 * 1024) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
@@ -465,19 +501,35 @@ static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out
 #ifndef D2D_TU_MODE
 #error "compile with -DD2D_TU_MODE=<D2D_MODE_*> (differt2d_b200/build.py)"
 #endif
+#ifndef D2D_TU_SOLVER
+#define D2D_TU_SOLVER 0  // 0: ImagePath kernels; 1: FermatPath / MinPath kernels (separate translation unit)
+#endif
 
+template <int MODE, int METHOD>
+static int launch_bwd_role(const KParams& p, int grid_role, const float* Zbar, const BwdOut& out, cudaStream_t stream) {
+    return grid_role == D2D_GRID_TRANSMITTERS ? launch_bwd_one<MODE, METHOD, true>(p, Zbar, out, stream)
+                                              : launch_bwd_one<MODE, METHOD, false>(p, Zbar, out, stream);
+}
+
+#if D2D_TU_SOLVER
+template <>
+int launch_bwd_solver_mode<D2D_TU_MODE>(const KParams& p, int grid_role, int method, const float* Zbar,
+                                        const BwdOut& out, cudaStream_t stream) {
+    if (method == D2D_METHOD_FERMAT) return launch_bwd_role<D2D_TU_MODE, D2D_METHOD_FERMAT>(p, grid_role, Zbar, out, stream);
+    if (method == D2D_METHOD_MINPATH) return launch_bwd_role<D2D_TU_MODE, D2D_METHOD_MINPATH>(p, grid_role, Zbar, out, stream);
+    return (int)cudaErrorInvalidValue;
+}
+#else
 template <>
 int launch_bwd_mode<D2D_TU_MODE>(const KParams& p, int grid_role, int method, const float* Zbar, const BwdOut& out,
                                  cudaStream_t stream) {
-    (void)method;
-    return grid_role == D2D_GRID_TRANSMITTERS ? launch_bwd_one<D2D_TU_MODE, true>(p, Zbar, out, stream)
-                                              : launch_bwd_one<D2D_TU_MODE, false>(p, Zbar, out, stream);
+    if (method != D2D_METHOD_IMAGE) return launch_bwd_solver_mode<D2D_TU_MODE>(p, grid_role, method, Zbar, out, stream);
+    return launch_bwd_role<D2D_TU_MODE, D2D_METHOD_IMAGE>(p, grid_role, Zbar, out, stream);
 }
 
 #if D2D_TU_MODE == D2D_MODE_HARD
 int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, const float* Zbar, const BwdOut& out,
                      cudaStream_t stream, long long* launches) {
-    if (method != D2D_METHOD_IMAGE) return (int)cudaErrorNotSupported;
     cudaError_t e;
     if (out.objects_bar && (e = cudaMemsetAsync(out.objects_bar, 0, sizeof(float) * 4 * p.N, stream)) != cudaSuccess) return (int)e;
     if (out.phis_bar && (e = cudaMemsetAsync(out.phis_bar, 0, sizeof(float) * p.N, stream)) != cudaSuccess) return (int)e;
@@ -499,6 +551,7 @@ int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, cons
     if (launches) *launches += 1;
     return rc;
 }
+#endif
 #endif
 
 }  // namespace d2d

@@ -28,6 +28,11 @@ template <int MODE>
 int launch_fwd_mode(const KParams& p, int grid_role, int method, float* Z, float* valid_out, cudaStream_t s);
 template <int MODE>
 int launch_bwd_mode(const KParams& p, int grid_role, int method, const float* Zbar, const BwdOut& out, cudaStream_t s);
+template <int MODE>
+int launch_bwd_solver_mode(const KParams& p, int grid_role, int method, const float* Zbar, const BwdOut& out, cudaStream_t s);
+template <> int launch_bwd_solver_mode<D2D_MODE_HARD>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
+template <> int launch_bwd_solver_mode<D2D_MODE_HARD_SIGMOID>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
+template <> int launch_bwd_solver_mode<D2D_MODE_SIGMOID>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
 template <> int launch_fwd_mode<D2D_MODE_HARD>(const KParams&, int, int, float*, float*, cudaStream_t);
 template <> int launch_fwd_mode<D2D_MODE_HARD_SIGMOID>(const KParams&, int, int, float*, float*, cudaStream_t);
 template <> int launch_fwd_mode<D2D_MODE_SIGMOID>(const KParams&, int, int, float*, float*, cudaStream_t);

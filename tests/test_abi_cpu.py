@@ -97,7 +97,9 @@ def test_argument_validation_without_gpu():
     p.max_order = 2
     assert lib.d2d_problem_num_candidates(C.byref(p)) == 785
     p.method = L.METHOD_FERMAT
-    assert lib.d2d_power_bwd(C.byref(p), None, None, None, None, None, None, None, None) == 2  # unsupported
+    # Fermat/MinPath reverse mode needs the x0 table, like the forward
+    assert lib.d2d_power_bwd(C.byref(p), None, None, None, None, None, None, None, None) == 1
+    assert b"x0" in lib.d2d_last_error()
 
 
 def test_no_cpu_fallback():

@@ -281,7 +281,10 @@ def test_cull_equals_nocull_sweep(name, alpha):
 
 @pytest.mark.parametrize("name", ["basic", "geojson_norm", "geojson"])
 def test_cull_equals_nocull_order3(name):
-    """Three-interaction chains exercise every stage of the cull (last, middle, first interaction)."""
+    """Three-interaction chains exercise every stage of the cull (last, middle, first interaction).
+    candidate_slices=1: with 20 412 candidates on 72 tiles the launcher would otherwise split the list over
+    several CTAs and combine partial sums with atomics (documented: summation order is then not the list
+    order), which is a different property from the cull's exactness."""
     sc = SCENES[name]
     n = 96 if name.startswith("geojson") else 256
     X, Y = H.jittered_grid(sc, n, n, seed=5)
@@ -289,10 +292,13 @@ def test_cull_equals_nocull_order3(name):
     xys, _, _ = sc.packed_objects()
     fixed = np.stack([p.xy for p in sc.transmitters.values()])
     for mode in MODES:
-        a = F.power_fwd(_cfg(mode, min_order=3, max_order=3, grid_cols=n), xys, fixed, grid, alpha=100.0, device="cuda")
-        b = F.power_fwd(_cfg(mode, min_order=3, max_order=3, grid_cols=n, cull=False), xys, fixed, grid, alpha=100.0,
-                        device="cuda")
+        kw = dict(min_order=3, max_order=3, grid_cols=n, candidate_slices=1)
+        a = F.power_fwd(_cfg(mode, **kw), xys, fixed, grid, alpha=100.0, device="cuda")
+        b = F.power_fwd(_cfg(mode, cull=False, **kw), xys, fixed, grid, alpha=100.0, device="cuda")
         assert torch.equal(a, b), (mode, int((a != b).sum()))
+        # automatic slicing: same map up to the summation order of the partial sums
+        c = F.power_fwd(_cfg(mode, min_order=3, max_order=3, grid_cols=n), xys, fixed, grid, alpha=100.0, device="cuda")
+        assert torch.allclose(a, c, rtol=1e-5, atol=1e-6 * float(a.abs().max())), mode
 
 
 def test_cull_equals_nocull_mixed_objects():
@@ -442,6 +448,89 @@ def test_minpath_ris_scene():
     assert close.mean() > 0.98
 
 
+def _solver_vjp_case(sc, method, mode, steps, *, min_order=0, max_order=2, n=6, m=7, alpha=100.0):
+    osc = H.oracle_scene_from_product(sc)
+    X, Y = H.jittered_grid(sc, n, m, seed=3)
+    X = np.ascontiguousarray(X, np.float32)
+    Y = np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    N = xys.shape[0]
+    C = sum((1 if k == 0 else N * (N - 1) ** (k - 1)) for k in range(min_order, max_order + 1))
+    x0 = np.random.default_rng(1234).random((C, max(max_order, 1)), dtype=np.float32)
+    Zbar = (0.5 + np.random.default_rng(7).random(X.shape)).astype(np.float32)
+    cfg = _cfg(mode, min_order=min_order, max_order=max_order, method=method, steps=steps, grid_cols=m, reduce_all=True)
+    got = F.power_bwd(cfg, xys, fixed, grid, Zbar.reshape(-1), kinds=kinds, phis=phis, x0=x0, alpha=alpha, device="cuda")
+    Zo, go = R.power_map_and_vjp(osc, X, Y, Zbar, method=method, min_order=min_order, max_order=max_order, x0=x0,
+                                 steps=steps, approx=mode != "hard", alpha=alpha,
+                                 function=mode if mode != "hard" else "hard_sigmoid")
+    want = {"Z": Zo, "grid": go["grid"], "objects": go["xys"], "phis": go["phis"], "fixed": go["fixed"],
+            "alpha": go["alpha"]}
+    err = {}
+    for k, w in want.items():
+        a = got[k].cpu().numpy().reshape(-1).astype(np.float64)
+        b = w.detach().numpy().reshape(-1).astype(np.float64)
+        err[k] = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) if np.abs(b).max() > 0 else np.abs(a).max()
+    return err
+
+
+@pytest.mark.parametrize("method", ["fermat", "minpath"])
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("steps,tol", [(1, 1e-4), (3, 1e-4), (10, 1e-3), (30, 1e-2)])
+def test_solver_vjp_through_adam_scan(method, mode, steps, tol):
+    """jax.grad through optimize.minimize's lax.scan (optimize.py:85-97) for FermatPath / MinPath,
+    w.r.t. grid points, object vertices, the transmitter and alpha — kernel (checkpointed reverse sweep, dual-number
+    Hessian-vector products) vs torch autograd with create_graph=True over the restated scan.  The Adam iterates
+    amplify last-bit differences exponentially in the step count (see test_solver_paths_vertex_scene), so the
+    bar is tight for short scans — where it pins the algebra of every term — and loosens with the length:
+    measured 1e-7..1e-5 at 1-10 steps, 1e-5..2e-3 at 30 steps (largest-entry relative)."""
+    err = _solver_vjp_case(H.generic_position(_vertex_scene()), method, mode, steps)
+    for k, e in err.items():
+        assert e < tol, (k, e, err)
+
+
+def test_solver_vjp_ris_long_scans():
+    """MinPath on the RIS scene (BASELINE config 5a): phi cotangent, and scans longer than the 32 x 32 checkpoint
+    grid (1100 steps: checkpoint stride 64, blocks re-run from the checkpoint).  Hard logic keeps the comparison
+    free of the activation slopes that amplify the iterate noise; MinPath converges to a flat minimum there."""
+    for steps, tol in [(5, 1e-4), (300, 1e-3), (1100, 1e-3)]:
+        err = _solver_vjp_case(H.generic_position(_ris_scene()), "minpath", "hard", steps, min_order=1, max_order=1)
+        for k, e in err.items():
+            assert e < tol, (steps, k, e, err)
+    err = _solver_vjp_case(H.generic_position(_ris_scene()), "minpath", "hard_sigmoid", 5, min_order=1, max_order=1,
+                           alpha=10.0)
+    for k, e in err.items():
+        assert e < 1e-3, (k, e, err)
+
+
+def test_solver_vjp_order3():
+    for method in ("fermat", "minpath"):
+        err = _solver_vjp_case(H.generic_position(_vertex_scene()), method, "hard_sigmoid", 10, max_order=3, n=3, m=3)
+        for k, e in err.items():
+            assert e < 2e-3, (method, k, e, err)
+
+
+def test_solver_autograd_function():
+    """power_map (the custom_vjp analogue) differentiates FermatPath maps end to end."""
+    sc = H.generic_position(_vertex_scene())
+    X, Y = H.jittered_grid(sc, 5, 6, seed=3)
+    xys, kinds, phis = sc.packed_objects()
+    dev = torch.device("cuda")
+    x0 = np.random.default_rng(1234).random((50, 2), dtype=np.float32)
+    xy_t = torch.tensor(xys, device=dev, requires_grad=True)
+    fixed = torch.tensor(np.stack([p.xy for p in sc.transmitters.values()]), device=dev, requires_grad=True)
+    grid = torch.tensor(np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32), device=dev, requires_grad=True)
+    cfg = _cfg("hard_sigmoid", max_order=2, method="fermat", steps=10, reduce_all=True)
+    Z = F.power_map(xy_t, fixed, grid, cfg=cfg, alpha=50.0, kinds=kinds, x0=x0)
+    Z.sum().backward()
+    ref = F.power_bwd(cfg, xys, fixed.detach(), grid.detach(), None, kinds=kinds, x0=x0, alpha=50.0, device=dev)
+    assert torch.allclose(Z.detach(), ref["Z"], rtol=1e-6)
+    assert torch.allclose(grid.grad, ref["grid"].reshape(-1, 2), rtol=1e-5, atol=1e-6)
+    assert torch.allclose(fixed.grad, ref["fixed"], rtol=1e-3, atol=1e-3 * ref["fixed"].abs().max().item())
+    assert torch.allclose(xy_t.grad, ref["objects"], rtol=1e-3, atol=1e-3 * ref["objects"].abs().max().item())
+
+
 def test_scene_api_solver_methods():
     sc = _vertex_scene()
     X, Y = sc.grid(24, 20)
@@ -449,5 +538,9 @@ def test_scene_api_solver_methods():
                                                    key=1234, approx=False,
                                                    filter_objects=lambda o: isinstance(o, d.Vertex))
     assert Z.shape == X.shape and Z.dtype == np.float32 and np.isfinite(Z).all() and (Z > 0).any()
+    Z2, dZ = sc.accumulate_on_receivers_grid_over_paths(X, Y, path_cls=d.FermatPath, reduce_all=True, max_order=1,
+                                                         key=1234, approx=False, value_and_grad=True,
+                                                         filter_objects=lambda o: isinstance(o, d.Vertex))
+    assert np.array_equal(Z2, Z) and dZ.shape == (*X.shape, 2) and np.isfinite(dZ).all() and (dZ != 0).any()
     with pytest.raises(TypeError):
         sc.accumulate_on_receivers_grid_over_paths(X, Y, path_cls=d.MinPath, reduce_all=True, approx=False)
