@@ -317,7 +317,7 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
     for_each_candidate<MODE, METHOD, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col) {
+        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
             bool has = false;
             float2 txb = make_float2(0.f, 0.f), rxb = make_float2(0.f, 0.f);
             float ab = 0.f;
@@ -328,10 +328,17 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
                 // light re-trace first (same code as the forward kernel); the reverse sweep is out of line
                 // and only runs for the few paths whose validity is non-zero
                 float2 X[K + 2];
-                float loss;
-                construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-                const float valid =
-                    validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+                float valid = 0.0f;
+                if constexpr (METHOD == D2D_METHOD_IMAGE) {
+                    float onx;
+                    const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
+                    if (image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx))
+                        valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
+                } else {
+                    float loss;
+                    construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
+                    valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+                }
                 if (valid != 0.0f) {
                     const float c = path_vjp<MODE, METHOD, K>(T, p, alpha, cd, tx, rx, col, zbar, has, txb, rxb, ab,
                                                               oa, occ_j, occ_bar);
@@ -377,7 +384,7 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
 }
 
 template <int MODE, int METHOD, bool TXGRID>
-__global__ void __launch_bounds__(kBlock) power_bwd_kernel(const KParams p, const float* __restrict__ Zbar,
+__global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(const KParams p, const float* __restrict__ Zbar,
                                                            const BwdOut out) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ DriverShared sh;

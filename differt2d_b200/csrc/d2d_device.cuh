@@ -130,10 +130,22 @@ __device__ __forceinline__ float act(float x, float alpha) {
     if (MODE == D2D_MODE_SIGMOID) {
         return 1.0f / (1.0f + expf(-z));  // logic.py:235
     }
-    float v = z + 3.0f;  // logic.py:255  relu6(z + 3) / 6
-    v = fmaxf(v, 0.0f);
-    v = fminf(v, 6.0f);
+    const float v = z + 3.0f;  // logic.py:255  relu6(z + 3) / 6
+    // the saturated branches are returned directly: 0/6 and 6/6 are exact, and an IEEE division with a zero
+    // numerator takes the 115-instruction slow path of div.rn (14 % of the forward kernel before this)
+    if (!(v > 0.0f)) return 0.0f;  // also NaN: relu6 via fmax/fmin maps NaN to 0
+    if (v >= 6.0f) return 1.0f;
     return v / 6.0f;
+}
+
+// act(x) == 0 exactly?  (the path is dead: a conjunct of is_valid vanishes)  Hard logic: the comparison is false.
+template <int MODE>
+__device__ __forceinline__ bool act_is_zero(float x, float alpha) {
+    if (MODE == D2D_MODE_HARD) return !(x >= 0.0f);
+    if (MODE == D2D_MODE_HARD_SIGMOID) return !(alpha * x + 3.0f > 0.0f);
+    const float z = alpha * x;
+    if (z > -87.0f) return false;  // expf(87) is finite: 1/(1+e) > 0
+    return act<MODE>(x, alpha) == 0.0f;
 }
 
 // d/dz of f at z = alpha*x (the VJP rules of jnp.minimum/maximum give 1/2 at the kinks)
@@ -197,19 +209,21 @@ __device__ __forceinline__ float2 back_project(const float2 point, const float2 
 
 // normalize — geometry.py:206-230
 __device__ __forceinline__ float2 normalize2(const float2 v, float& len) {
-    len = sqrtf(v.x * v.x + v.y * v.y);
-    if (len == 0.0f) len = 1.0f;
+    const float sq = v.x * v.x + v.y * v.y;
+    if (sq == 0.0f) {  // |v| == 0 -> v / 1 == v exactly; taken apart because sqrt.rn(0) and div.rn(0, .) both
+        len = 1.0f;    // leave the fast path of their IEEE expansions (zero-length closure walls hit this often)
+        return v;
+    }
+    len = sqrtf(sq);
     return make_float2(v.x / len, v.y / len);
 }
 
-// Interactable.evaluate_cartesian — Wall geometry.py:641-650, RIS :698-711, Vertex :416-419
-__device__ __forceinline__ float residual(const int kind, const float2 a, const float2 b, const float2 c,
-                                          const float4 w1, const float2 sc) {
+// Interactable.evaluate_cartesian — Wall geometry.py:641-650, RIS :698-711, Vertex :416-419 — from the unit
+// directions i = normalize(b - a) and r = normalize(c - b)
+__device__ __forceinline__ float residual_dirs(const int kind, const float2 i, const float2 r, const float4 w1,
+                                               const float2 sc) {
     if (kind == D2D_KIND_VERTEX) return 0.0f;
-    float l;
-    const float2 r = normalize2(make_float2(c.x - b.x, c.y - b.y), l);
     if (kind == D2D_KIND_WALL) {
-        const float2 i = normalize2(make_float2(b.x - a.x, b.y - a.y), l);
         const float c2 = 2.0f * (i.x * w1.x + i.y * w1.y);
         const float ex = r.x - (i.x - c2 * w1.x);
         const float ey = r.y - (i.y - c2 * w1.y);
@@ -222,10 +236,21 @@ __device__ __forceinline__ float residual(const int kind, const float2 a, const 
     return ds * ds + dc * dc;
 }
 
+__device__ __forceinline__ float residual(const int kind, const float2 a, const float2 b, const float2 c,
+                                          const float4 w1, const float2 sc) {
+    if (kind == D2D_KIND_VERTEX) return 0.0f;
+    float l;
+    const float2 r = normalize2(make_float2(c.x - b.x, c.y - b.y), l);
+    float2 i = make_float2(0.f, 0.f);
+    if (kind == D2D_KIND_WALL) i = normalize2(make_float2(b.x - a.x, b.y - a.y), l);
+    return residual_dirs(kind, i, r, w1, sc);
+}
+
 // Wall.cartesian_to_parametric — geometry.py:589-598
 __device__ __forceinline__ float to_parametric(const float2 x, const float4 w0, const float4 w1) {
     const float ox = x.x - w0.x, oy = x.y - w0.y;
-    return (w0.z * ox + w0.w * oy) / w1.z;
+    const float num = w0.z * ox + w0.w * oy;
+    return num == 0.0f ? num : num / w1.z;  // (+-0 / tt == +-0 exactly, tt > 0; avoids div.rn's slow path)
 }
 
 // path_length — geometry.py:176-203
@@ -243,7 +268,7 @@ __device__ __forceinline__ float path_length(const float2 (&X)[NP]) {
 }
 
 // Exact pre-activation of one segment/object test — geometry.py:153-173 with tol = 0.005
-__device__ __forceinline__ float hit_exact(const float a, const float b, const float d) {
+static __device__ __forceinline__ float hit_exact(const float a, const float b, const float d) {
     if (d == 0.0f) return -CUDART_INF_F;  // t = +inf  ->  (1+tol) - inf
     const float ta = a / d, tb = b / d;
     const float h = fminf(fminf(ta + kTolSeg, kHiSeg - ta), fminf(tb + kTolSeg, kHiSeg - tb));

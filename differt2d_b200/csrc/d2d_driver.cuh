@@ -12,7 +12,11 @@
 //      error of the exact per-thread evaluation, so a culled candidate has validity EXACTLY 0 for every
 //      point of the tile: results are unchanged, bit for bit (tests/test_gpu_parity.py).
 //   2. ordered compaction of the survivors into shared memory (per-warp segments, list order kept);
-//   3. TRACE: every thread evaluates the surviving candidates for its own grid point, exactly.
+//   3. WARP CULL: each warp re-tests the survivors (one per lane) against the bounding box of ITS 32 points
+//      (16 x 2 in a tiled grid) with the s-range rule on the last interaction only, reusing the error bound the
+//      tile-level test established (it holds for every point of the tile, hence for the sub-box's corners);
+//      the warp then walks the set bits of the ballot, still in list order;
+//   4. TRACE: every thread evaluates the remaining candidates for its own grid point, exactly.
 //
 // The culled work still counts as algorithmic work ("no early-out credit").
 #pragma once
@@ -22,6 +26,14 @@
 namespace d2d {
 
 constexpr int kBlock = 128;
+// resident CTAs per SM the kernels are compiled for (register caps 64 / 96 per thread): occupancy hides the
+// instruction-fetch and fixed-latency stalls that dominate these branchy FP32 kernels (profiles/)
+#ifndef D2D_FWD_MIN_CTAS
+#define D2D_FWD_MIN_CTAS 8
+#endif
+#ifndef D2D_BWD_MIN_CTAS
+#define D2D_BWD_MIN_CTAS 5
+#endif
 constexpr int kTileCols = 16;
 constexpr int kTileRows = 8;
 
@@ -29,6 +41,7 @@ struct Tile {
     long long r;      // grid-point index of this thread (row-major), valid when `active`
     bool active;
     float4 bbox;      // xmin, ymin, xmax, ymax over the tile's active points
+    float4 wbox;      // same over this thread's warp (inverted / infinite when the warp has no active point)
     float scale;      // max |coordinate| over tile, fixed points and objects (for error bounds)
 };
 
@@ -37,6 +50,8 @@ struct DriverShared {
     float red[4][4];         // per-warp partials
     int wcount[2][4];        // survivors per warp segment, double buffered
     int4 list[2][kBlock];    // packed survivors: (c0 | c1 << 16, c2 | c3 << 16, index lo, index hi)
+    float4 aux[2][kBlock];   // per survivor: apex (image of the fixed point through all objects) x, y; s-tolerance of
+                             // the last interaction for the warp-level test (+inf: no test possible); unused
 };
 
 // CTAs along x for a problem (host side)
@@ -78,6 +93,7 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
         xmax = fmaxf(xmax, __shfl_xor_sync(0xffffffffu, xmax, o));
         ymax = fmaxf(ymax, __shfl_xor_sync(0xffffffffu, ymax, o));
     }
+    t.wbox = make_float4(xmin, ymin, xmax, ymax);
     const int warp = tid >> 5, lane = tid & 31;
     if (lane == 0) {
         sh.red[warp][0] = xmin; sh.red[warp][1] = ymin; sh.red[warp][2] = xmax; sh.red[warp][3] = ymax;
@@ -130,7 +146,9 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
 template <int K>
 __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (&c)[K > 0 ? K : 1],
                                                   const float2 (&I)[K + 1], const float4 bbox, const float scale,
-                                                  const float xz, const float loss_dead /* tol_loss - xz */) {
+                                                  const float xz, const float loss_dead /* tol_loss - xz */,
+                                                  float& tol_last) {
+    tol_last = CUDART_INF_F;
     if (!(xz > -CUDART_INF_F)) return true;
     const float eps = 5.9604645e-8f;
     const float S = scale;
@@ -160,17 +178,19 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         float smin = CUDART_INF_F, smax = -CUDART_INF_F, gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
         float unmin = CUDART_INF_F, U1 = 0.f, V1 = 0.f, uxm = 0.f, uym = 0.f, u2m = 0.f;
         int pos = 0, neg = 0;
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            if (q >= npts) break;
-            const float ux = pts[q].x - A.x, uy = pts[q].y - A.y;
-            const float vx = w0.x - pts[q].x, vy = w0.y - pts[q].y;
+        // rolled on purpose: these kernels are instruction-fetch bound (profiles/), and the unrolled corner loop
+        // made the cull a 24 KB straight line that every warp streamed through once per candidate
+#pragma unroll 1
+        for (int q = 0; q < npts; ++q) {
+            const float2 pq = q == 0 ? pts[0] : (q == 1 ? pts[1] : (q == 2 ? pts[2] : pts[3]));
+            const float ux = pq.x - A.x, uy = pq.y - A.y;
+            const float vx = w0.x - pq.x, vy = w0.y - pq.y;
             const float un = fmaf(ux, w1.x, uy * w1.y);
             const float vn = fmaf(vx, w1.x, vy * w1.y);
             pos += un > 0.f;
             neg += un < 0.f;
             const float g = vn / un;
-            const float Xx = fmaf(g, ux, pts[q].x), Xy = fmaf(g, uy, pts[q].y);
+            const float Xx = fmaf(g, ux, pq.x), Xy = fmaf(g, uy, pq.y);
             const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) / w1.z;
             smin = fminf(smin, s); smax = fmaxf(smax, s);
             gmin = fminf(gmin, g); gmax = fmaxf(gmax, g);
@@ -193,6 +213,7 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         const float ds = (fabsf(w0.z) * dXx + fabsf(w0.w) * dXy) / w1.z + 4.0f * eps * smag;
         const float tol = 2.5f * ds + 1e-6f;
         if (!(tol < CUDART_INF_F)) return true;
+        if (i == K - 1) tol_last = tol;  // valid for every point of the tile: reused by warp_may_be_valid
         const float lo = xz - tol, hi = 1.0f - xz + tol;
         if (smax < lo || smin > hi) return false;                  // rule (1)
         // g-range and segment lengths for rules (2) and (3)
@@ -206,7 +227,9 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         const float seg_bA = g1_abs_min * un_eff;   // |X - A| >= |1 + g| |u.n|
         if (!(seg_pb >= Lmin && seg_bA >= Lmin)) lens_ok = false;
         if (deg_pending) {  // the zero-length object(s) between p and this X: previous point is X, distance |p - X|
-            if (seg_pb >= Lmin) deg_dead = true;
+            // rule (3) only needs the two COMPUTED points to differ (any non-zero vector normalises to |i_hat|^2 =
+            // 1 +- 4 ulp): true distance minus both evaluation errors, not the direction accuracy of rule (2)
+            if (seg_pb > dXx + dXy + 16.0f * eps * S + 1e-15f) deg_dead = true;
             deg_pending = false;
         }
         // the reachable part of this object becomes the point set of the next (earlier) interaction
@@ -226,7 +249,7 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         }
         const float dx = fmaxf(fmaxf(xl - I[0].x, I[0].x - xh), 0.0f);
         const float dy = fmaxf(fmaxf(yl - I[0].y, I[0].y - yh), 0.0f);
-        if (fmaxf(dx, dy) - dev >= Lmin) deg_dead = true;
+        if (fmaxf(dx, dy) - dev > 16.0f * eps * S + 1e-15f) deg_dead = true;
     }
     if (all_walls) {
         if (any_deg) {
@@ -238,6 +261,33 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
     return true;
 }
 
+// Warp-level refinement of rule (1) for the LAST interaction: the s-range over the warp's own bounding box
+// (a sub-box of the tile's), evaluated exactly like the tile-level test at its corners; `tol` is the tile-level
+// error bound (every quantity it is built from is a maximum / minimum over the whole tile, and the tile-level
+// test has already established that u.n keeps its sign there).  false => validity exactly 0 for all 32 points.
+__device__ __forceinline__ bool warp_may_be_valid(const float4 w0, const float4 w1, const float2 A, const float4 box,
+                                                  const float tol, const float xz) {
+    if (!(tol < CUDART_INF_F)) return true;
+    float smin = CUDART_INF_F, smax = -CUDART_INF_F;
+    bool nan = false;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float px = (q & 1) ? box.z : box.x, py = (q & 2) ? box.w : box.y;
+        const float ux = px - A.x, uy = py - A.y;
+        const float vx = w0.x - px, vy = w0.y - py;
+        const float un = fmaf(ux, w1.x, uy * w1.y);
+        const float vn = fmaf(vx, w1.x, vy * w1.y);
+        const float g = vn / un;
+        const float Xx = fmaf(g, ux, px), Xy = fmaf(g, uy, py);
+        const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) / w1.z;
+        nan = nan || !(s == s);
+        smin = fminf(smin, s);
+        smax = fmaxf(smax, s);
+    }
+    if (nan) return true;
+    return !(smax < xz - tol || smin > 1.0f - xz + tol);
+}
+
 // number of candidates of order K over m visitable objects
 __device__ __forceinline__ long long order_count(const int K, const int m) {
     if (K == 0) return 1;
@@ -247,9 +297,10 @@ __device__ __forceinline__ long long order_count(const int K, const int m) {
     return c;
 }
 
-// Walks all candidates of order K for the fixed point `fx`; calls visit(cd, col) — uniformly over the
-// CTA — for every candidate that survives the tile cull, in list order.  `col0` = column of the first
-// candidate of this order in the global list.
+// Walks all candidates of order K for the fixed point `fx`; calls visit(cd, col, apex) — uniformly over a
+// WARP — for every candidate that survives the tile and warp culls, in list order.  `col0` = column of the first
+// candidate of this order in the global list; `apex` = image of fx through the candidate's objects (ImagePath on a
+// receivers grid only, otherwise unspecified).
 template <int MODE, int METHOD, int K, bool TXGRID, class Visit>
 __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KParams& p, const Tile& tile,
                                                    DriverShared& sh, const float alpha, const float2 fx,
@@ -260,17 +311,20 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     if constexpr (K == 0) {
         Cand<0> cd;
         cd.c[0] = 0;
-        if (blockIdx.y == 0) visit(cd, col0);  // uniform over the CTA
+        if (blockIdx.y == 0) visit(cd, col0, fx);  // uniform over the CTA
         return;
     }
     constexpr int KK = K > 0 ? K : 1;
-    const bool cull = (METHOD == D2D_METHOD_IMAGE) && !TXGRID && p.cull;
+    constexpr bool kApex = (METHOD == D2D_METHOD_IMAGE) && !TXGRID;
+    const bool cull = kApex && p.cull;
     const float xz = x_zero<MODE>(alpha);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // candidate slices (point-to-point links with huge candidate lists): CTA y walks chunks y, y + slices, ...
     for (long long base = (long long)blockIdx.y * kBlock; base < Ck; base += (long long)kBlock * gridDim.y) {
         const long long idx = base + tid;
         bool keep = false;
+        float2 apex = fx;
+        float tol_last = CUDART_INF_F;
         int c[KK];
 #pragma unroll
         for (int i = 0; i < KK; ++i) c[i] = 0;
@@ -293,12 +347,13 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
                 prev = pos;
             }
             keep = true;
-            if (cull) {
+            if (kApex) {
                 float2 I[K + 1];
                 I[0] = fx;
 #pragma unroll
                 for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[c[i]], T.w1[c[i]]);
-                keep = tile_may_be_valid<K>(T, c, I, tile.bbox, tile.scale, xz, p.tol - xz);
+                apex = I[K];
+                if (cull) keep = tile_may_be_valid<K>(T, c, I, tile.bbox, tile.scale, xz, p.tol - xz, tol_last);
             }
         }
         // ordered compaction: per-warp segments keep list order
@@ -309,22 +364,53 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
                 make_int4(c[0] | ((K > 1 ? c[K > 1 ? 1 : 0] : 0) << 16),
                           (K > 2 ? c[K > 2 ? 2 : 0] : 0) | ((K > 3 ? c[K > 3 ? 3 : 0] : 0) << 16),
                           (int)(idx & 0xffffffffLL), (int)(idx >> 32));
+            if (kApex) sh.aux[buf][warp * 32 + off] = make_float4(apex.x, apex.y, tol_last, 0.f);
         }
         if (lane == 0) sh.wcount[buf][warp] = __popc(ballot);
         __syncthreads();
+        // survivors of the chunk, addressed contiguously across the four per-warp segments (list order)
+        const int n0 = sh.wcount[buf][0], n1 = n0 + sh.wcount[buf][1], n2 = n1 + sh.wcount[buf][2],
+                  n3 = n2 + sh.wcount[buf][3];
+        auto slot_of = [&](const int q) {
+            const int w = (q >= n0) + (q >= n1) + (q >= n2);
+            return w * 32 + (q - (w == 0 ? 0 : (w == 1 ? n0 : (w == 2 ? n1 : n2))));
+        };
 #pragma unroll 1
-        for (int w = 0; w < kBlock / 32; ++w) {
-            const int n = sh.wcount[buf][w];
+        for (int q0 = 0; q0 < n3; q0 += 32) {
+            const int nq = min(32, n3 - q0);
+            unsigned todo = nq >= 32 ? 0xffffffffu : ((1u << nq) - 1u);
+            if (cull) {  // warp-level refinement: lane q tests survivor q0 + q against this warp's box
+                bool wk = false;
+                if (lane < nq && tile.wbox.x <= tile.wbox.z) {  // (a warp without active points skips everything)
+                    const int sl = slot_of(q0 + lane);
+                    const int4 e = sh.list[buf][sl];
+                    const float4 a = sh.aux[buf][sl];
+                    int jl = e.x & 0xffff;
+                    if (K == 2) jl = (e.x >> 16) & 0xffff;
+                    if (K == 3) jl = e.y & 0xffff;
+                    if (K == 4) jl = (e.y >> 16) & 0xffff;
+                    wk = warp_may_be_valid(T.w0[jl], T.w1[jl], make_float2(a.x, a.y), tile.wbox, a.z, xz);
+                }
+                todo = __ballot_sync(0xffffffffu, wk);
+            }
 #pragma unroll 1
-            for (int q = 0; q < n; ++q) {
-                const int4 e = sh.list[buf][w * 32 + q];
+            while (todo) {
+                const int q = __ffs(todo) - 1;
+                todo &= todo - 1;
+                const int sl = slot_of(q0 + q);
+                const int4 e = sh.list[buf][sl];
                 Cand<K> cd;
                 cd.c[0] = e.x & 0xffff;
                 if (K > 1) cd.c[K > 1 ? 1 : 0] = (e.x >> 16) & 0xffff;
                 if (K > 2) cd.c[K > 2 ? 2 : 0] = e.y & 0xffff;
                 if (K > 3) cd.c[K > 3 ? 3 : 0] = (e.y >> 16) & 0xffff;
                 const long long ci = ((long long)(unsigned)e.z) | ((long long)e.w << 32);
-                visit(cd, col0 + ci);
+                float2 ax = fx;
+                if (kApex) {
+                    const float4 a = sh.aux[buf][sl];
+                    ax = make_float2(a.x, a.y);
+                }
+                visit(cd, col0 + ci, ax);
             }
         }
         buf ^= 1;  // the next chunk fills the other buffer: one barrier per chunk

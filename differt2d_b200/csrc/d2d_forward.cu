@@ -19,12 +19,21 @@ __device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, c
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
     for_each_candidate<MODE, METHOD, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col) {
+        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
             if (!tile.active) return;
             float2 X[K + 2];
-            float loss;
-            construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-            const float valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+            float valid;
+            if constexpr (METHOD == D2D_METHOD_IMAGE) {
+                // construction fused with on_objects: most paths that reach this point die at their last interaction
+                float onx;
+                const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
+                if (!image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx)) return;
+                valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
+            } else {
+                float loss;
+                construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
+                valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+            }
             if (valid != 0.0f) {
                 float r;
                 acc = acc + valid * path_value<K>(p, X, r);  // scene.py:1909
@@ -34,7 +43,7 @@ __device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, c
 }
 
 template <int MODE, int METHOD, bool TXGRID>
-__global__ void __launch_bounds__(kBlock) power_fwd_kernel(const KParams p, float* __restrict__ Z,
+__global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(const KParams p, float* __restrict__ Z,
                                                            float* __restrict__ valid_out) {
     extern __shared__ __align__(16) unsigned char smem[];
     __shared__ DriverShared sh;

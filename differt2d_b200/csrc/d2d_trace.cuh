@@ -30,6 +30,64 @@ __device__ __forceinline__ void image_path(const SceneTab& T, const Cand<K>& cd,
     }
 }
 
+// ImagePath construction fused with Path.on_objects, last interaction first (the order of the reference's own
+// backward scan, geometry.py:1093-1107): the walk stops as soon as one interaction point lies so far off its
+// object that act(s) or act(1 - s) is exactly 0 — is_valid is then exactly 0 whatever the rest of the path
+// does.  Same operations, same order, same roundings as image_path() + on_objects_x() for the paths that
+// survive.  `apex` = image of the transmitter through all K objects (I[K]); the earlier images are only
+// built for paths that pass the last interaction.  Returns false for a dead path; X and onx are then partial.
+template <int MODE, int K>
+__device__ __forceinline__ bool image_path_on(const SceneTab& T, const Cand<K>& cd, const float2 tx, const float2 rx,
+                                              const float2 apex, const float alpha, float2 (&X)[K + 2], float& onx) {
+    X[0] = tx;
+    X[K + 1] = rx;
+    onx = CUDART_INF_F;
+    if constexpr (K == 0) return true;
+    float2 q = rx;
+    {
+        const int j = cd.c[K > 0 ? K - 1 : 0];
+        const float4 w0 = T.w0[j], w1 = T.w1[j];
+        q = back_project(q, apex, w0, w1);
+        X[K] = q;
+        if (T.kind[j] != D2D_KIND_VERTEX) {
+            const float s = to_parametric(q, w0, w1);
+            float x = fminf(s, 1.0f - s);
+            if (s != s) x = -CUDART_INF_F;
+            if (act_is_zero<MODE>(x, alpha)) return false;
+            onx = x;
+        }
+    }
+    if constexpr (K > 1) {
+        float2 I[K];
+        I[0] = tx;
+#pragma unroll
+        for (int i = 0; i + 1 < K; ++i) I[i + 1] = mirror(I[i], T.w0[cd.c[i]], T.w1[cd.c[i]]);
+#pragma unroll
+        for (int i = K - 2; i >= 0; --i) {
+            const int j = cd.c[i];
+            const float4 w0 = T.w0[j], w1 = T.w1[j];
+            q = back_project(q, I[i + 1], w0, w1);
+            X[i + 1] = q;
+            if (T.kind[j] == D2D_KIND_VERTEX) continue;
+            const float s = to_parametric(q, w0, w1);
+            float x = fminf(s, 1.0f - s);
+            if (s != s) x = -CUDART_INF_F;
+            if (act_is_zero<MODE>(x, alpha)) return false;
+            onx = fminf(onx, x);
+        }
+    }
+    return true;
+}
+
+// image of `tx` through all K objects of the candidate (the apex seen from the receiver side)
+template <int K>
+__device__ __forceinline__ float2 image_apex(const SceneTab& T, const Cand<K>& cd, const float2 tx) {
+    float2 a = tx;
+#pragma unroll
+    for (int i = 0; i < K; ++i) a = mirror(a, T.w0[cd.c[i]], T.w1[cd.c[i]]);
+    return a;
+}
+
 // Path.on_objects in pre-activation form — geometry.py:821-854, 589-621.  +inf when no object
 // contributes a comparison (order 0, or only vertices): `true_value`.
 template <int K>
@@ -47,51 +105,33 @@ __device__ __forceinline__ float on_objects_x(const SceneTab& T, const Cand<K>& 
     return onx;
 }
 
-// sum of interaction residuals — geometry.py:1077-1084
+// sum of interaction residuals — geometry.py:1077-1084.  Interaction i uses i_hat = normalize(X[i+1] - X[i]) and
+// r_hat = normalize(X[i+2] - X[i+1]) (geometry.py:641-650): the r_hat of one interaction is the i_hat of the next
+// (same function of the same inputs, hence the same bits), so the K + 1 segment directions are normalised once.
 template <int K>
 __device__ __forceinline__ float path_loss(const SceneTab& T, const Cand<K>& cd, const float2 (&X)[K + 2]) {
     float loss = 0.0f;
+    if (K == 0) return loss;
+    float l;
+    float2 dir = normalize2(make_float2(X[1].x - X[0].x, X[1].y - X[0].y), l);
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const int j = cd.c[i];
-        loss = loss + residual(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j]);
+        const float2 r = normalize2(make_float2(X[i + 2].x - X[i + 1].x, X[i + 2].y - X[i + 1].y), l);
+        loss = loss + residual_dirs(T.kind[j], dir, r, T.w1[j], T.sc[j]);
+        dir = r;
     }
     return loss;
 }
 
-// Occlusion of one segment by objects j in [j0, j1) — geometry.py:887-904 + :153-173.
-// Fast path per test: canonical a, b, d; approximate parameters through one MUFU.RCP and two FMAs;
-// the exact IEEE divisions only run when the test could raise the running maximum `interx`.
-template <int MODE, bool TRACK>
-__device__ __forceinline__ void occlude_range(const SceneTab& T, const int j0, const int j1, const float2 P,
-                                              const float2 B, const float alpha, const float xz,
-                                              float& interx, float& cthr, bool& alive, int& arg_j) {
-#pragma unroll 4
-    for (int j = j0; j < j1 && alive; ++j) {
-        const float4 w = T.w2[j];
-        const float Cx = w.x - P.x, Cy = w.y - P.y;
-        const float a = B.y * Cx - B.x * Cy;
-        const float b = w.z * Cy - w.w * Cx;
-        const float d = w.w * B.x - w.z * B.y;
-        const float r = rcp_approx(d);
-        const float qa = fmaf(a, r, -0.5f);
-        const float qb = fmaf(b, r, -0.5f);
-        const float m = fmaxf(fabsf(qa), fabsf(qb));
-        if (!(m >= cthr)) {
-            const float hx = hit_exact(a, b, d);
-            if (hx > interx) {
-                interx = hx;
-                if (TRACK) arg_j = j;
-                cthr = filter_threshold(fmaxf(hx, xz));
-                // the path is dead once `intersects` is exactly true / 1.0
-                if (MODE == D2D_MODE_HARD) alive = !(hx >= 0.0f);
-                else alive = !(act<MODE>(hx, alpha) == 1.0f);
-            }
-        }
-    }
-}
-
-// Path.intersects_with_objects in pre-activation form.  Returns interx (-inf: `false_value`).
+// Path.intersects_with_objects in pre-activation form (geometry.py:887-904 + :153-173).  Returns interx
+// (-inf: `false_value`).  The double loop runs object-major: one shared-memory read of the object serves the
+// K + 1 segments, whose tests are independent instruction streams (ILP), and the whole fold is ONE loop body
+// (the segment-major form needed 3 (K + 1) unrolled range loops: 9x the code at K = 2).  max is exact and
+// commutative, so the fold order does not matter; for the reverse sweep (TRACK) ties between tests keep the
+// first arg-max in the reference's (segment, object) order.
+// Fast path per test: canonical a, b, d; approximate parameters through one MUFU.RCP and two FMAs; the exact
+// IEEE divisions (hit_exact, out of line) only run when the test could raise the running maximum `interx`.
 template <int MODE, int K, bool TRACK>
 __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, const Cand<K>& cd,
                                               const float2 (&X)[K + 2], const float alpha, bool& alive,
@@ -99,18 +139,40 @@ __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, co
     float interx = -CUDART_INF_F;
     const float xz = x_zero<MODE>(alpha);
     float cthr = filter_threshold(xz);
+    float2 B[K + 1];
+    int sa[K + 1], sb[K + 1];
 #pragma unroll
     for (int i = 0; i <= K; ++i) {
-        const int sa = (i > 0) ? cd.c[i - 1] : -1;
-        const int sb = (i < K) ? cd.c[i] : -1;
-        const int lo = min(sa, sb), hi = max(sa, sb);  // lo may be -1; sa != sb unless both -1
-        const float2 P = X[i];
-        const float2 B = make_float2(X[i].x - X[i + 1].x, X[i].y - X[i + 1].y);
-        const float before = interx;
-        occlude_range<MODE, TRACK>(T, 0, lo < 0 ? 0 : lo, P, B, alpha, xz, interx, cthr, alive, arg_j);
-        occlude_range<MODE, TRACK>(T, lo + 1, hi < 0 ? 0 : hi, P, B, alpha, xz, interx, cthr, alive, arg_j);
-        occlude_range<MODE, TRACK>(T, hi + 1, N, P, B, alpha, xz, interx, cthr, alive, arg_j);
-        if (TRACK && interx != before) arg_seg = i;
+        B[i] = make_float2(X[i].x - X[i + 1].x, X[i].y - X[i + 1].y);
+        sa[i] = (i > 0) ? cd.c[i > 0 ? i - 1 : 0] : -1;  // the segment's own end objects are skipped
+        sb[i] = (i < K) ? cd.c[i < K ? i : 0] : -1;
+    }
+#pragma unroll 1
+    for (int j = 0; j < N; ++j) {
+        const float4 w = T.w2[j];
+#pragma unroll
+        for (int i = 0; i <= K; ++i) {
+            if (j == sa[i] || j == sb[i]) continue;
+            const float Cx = w.x - X[i].x, Cy = w.y - X[i].y;
+            const float a = B[i].y * Cx - B[i].x * Cy;
+            const float b = w.z * Cy - w.w * Cx;
+            const float d = w.w * B[i].x - w.z * B[i].y;
+            const float r = rcp_approx(d);
+            const float qa = fmaf(a, r, -0.5f);
+            const float qb = fmaf(b, r, -0.5f);
+            const float m = fmaxf(fabsf(qa), fabsf(qb));
+            if (!(m >= cthr)) {
+                const float hx = hit_exact(a, b, d);
+                if (hx > interx || (TRACK && hx == interx && i < arg_seg)) {
+                    interx = hx;
+                    if (TRACK) { arg_j = j; arg_seg = i; }
+                    cthr = filter_threshold(fmaxf(hx, xz));
+                    // the path is dead once `intersects` is exactly true / 1.0
+                    if (MODE == D2D_MODE_HARD) alive = !(hx >= 0.0f);
+                    else alive = !(act<MODE>(hx, alpha) == 1.0f);
+                }
+            }
+        }
         if (!alive) break;
     }
     return interx;
@@ -129,10 +191,21 @@ __device__ __forceinline__ float path_value(const KParams& p, const float2 (&X)[
 // the path loss (two normalisations per interaction) is only evaluated for paths that lie on their objects:
 // LAZY_LOSS = true computes it here from X (Image / Fermat), false takes the solver's value (MinPath).
 template <int MODE, int K, bool LAZY_LOSS>
+__device__ __forceinline__ float validity_from_onx(const SceneTab& T, const KParams& p, const float alpha,
+                                                   const Cand<K>& cd, const float2 (&X)[K + 2], float loss,
+                                                   const float onx);
+
+template <int MODE, int K, bool LAZY_LOSS>
 __device__ __forceinline__ float validity(const SceneTab& T, const KParams& p, const float alpha,
                                           const Cand<K>& cd, const float2 (&X)[K + 2], float loss) {
+    return validity_from_onx<MODE, K, LAZY_LOSS>(T, p, alpha, cd, X, loss, on_objects_x<K>(T, cd, X));
+}
+
+template <int MODE, int K, bool LAZY_LOSS>
+__device__ __forceinline__ float validity_from_onx(const SceneTab& T, const KParams& p, const float alpha,
+                                                   const Cand<K>& cd, const float2 (&X)[K + 2], float loss,
+                                                   const float onx) {
     // 1. on_objects
-    const float onx = on_objects_x<K>(T, cd, X);
     float a_on = 1.0f;
     if (MODE == D2D_MODE_HARD) {
         if (!(onx >= 0.0f)) return 0.0f;
