@@ -7,7 +7,8 @@ zero length; TX = bbox NW corner), ImagePath orders 0-2 (785 candidates), smooth
 (hard_sigmoid, alpha = 100), forward power map + VJP (cotangents of the receiver coordinates, object
 vertices, TX position and alpha), on a receiver grid of 1024 x 1024 points PER GPU (weak scaling:
 N GPUs trace a (1024 N) x 1024 grid, row-sharded, one NCCL all-reduce of the scene-parameter
-cotangents per step).  A "step" = one forward launch + one backward (recompute) launch.
+cotangents per step).  A "step" = one forward launch + one backward launch, as jax.vjp runs them: the forward
+also writes the activity mask (1 bit per warp x candidate, 3 MB), the backward re-traces the paths it marks.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--coords raw|normalised]
 
@@ -261,6 +262,9 @@ def main() -> None:
 
     # device-resident step through the C ABI (device pointers, caller's stream)
     pk = F._Packed(cfg, xys_d, None, None, fixed_d, grid, ALPHA, None, dev)
+    # the VJP's only residual: one activity bit per (warp of 32 receivers, candidate), written by the forward
+    # launch of the step and read by its backward launch (the custom_vjp residual)
+    mask = pk.new_mask()
     Z = torch.empty(R, device=dev)
     gbar = torch.empty(R, 2, device=dev)
     pbar = torch.zeros(n_obj * 4 + n_obj + 2 * T + 1, device=dev)  # objects | phis | fixed | alpha, one NCCL buffer

@@ -59,12 +59,13 @@ class D2DProblem(C.Structure):
         ("grad_mode", C.c_int32),
         ("no_cull", C.c_int32),
         ("candidate_slices", C.c_int32),
+        ("active_mask", C.c_void_p),
     ]
 
 
 EXPORTS = [
     "d2d_problem_defaults", "d2d_candidates_count", "d2d_candidates_host", "d2d_candidates_device",
-    "d2d_problem_num_candidates", "d2d_power_fwd", "d2d_power_bwd", "d2d_power_host", "d2d_launch_count",
+    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_power_host", "d2d_launch_count",
     "d2d_fma_peak_launch", "d2d_last_error", "d2d_abi_version",
 ]
 
@@ -86,6 +87,8 @@ def lib() -> C.CDLL:
     vp = C.c_void_p
     L.d2d_problem_defaults.argtypes = [P]
     L.d2d_problem_defaults.restype = None
+    L.d2d_active_mask_words.argtypes = [P]
+    L.d2d_active_mask_words.restype = C.c_int64
     L.d2d_candidates_count.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32]
     L.d2d_candidates_count.restype = C.c_int64
     L.d2d_candidates_host.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32, vp]

@@ -179,6 +179,8 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
         if (want > 1) k.slices = (int)want;
     }
     if (k.slices > 65535) return fail(D2D_ERR_INVALID_ARGUMENT, "candidate_slices must be <= 65535");
+    k.mask = p->active_mask;
+    k.mask_wpw = (total + 31) / 32;
     return D2D_OK;
 }
 
@@ -271,6 +273,12 @@ int64_t d2d_problem_num_candidates(const D2DProblem* p) {
     d2d::KParams k;
     if (pack(p, k) != D2D_OK) return -1;
     return k.C_total;
+}
+
+int64_t d2d_active_mask_words(const D2DProblem* p) {
+    d2d::KParams k;
+    if (pack(p, k) != D2D_OK) return -1;
+    return (int64_t)k.T * d2d::num_tile_blocks(k) * 4 * k.mask_wpw;
 }
 
 int d2d_power_fwd(const D2DProblem* p, float* Z, float* valid_out, void* stream) {
@@ -370,13 +378,20 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
     dp.x0 = hp->x0 ? (const float*)(din + o_x0) : nullptr;
     // output arena
     const bool want_bwd = grid_bar || objects_bar || phis_bar || fixed_bar || alpha_bar;
+    const long long mask_words = want_bwd ? d2d_active_mask_words(&dp) : 0;
+    if (mask_words < 0) return D2D_ERR_INVALID_ARGUMENT;
     const size_t q_z = 0, q_gb = q_z + al(Tout * R * 4), q_ob = q_gb + al(grid_bar ? Tout * R * 8 : 0),
-                 q_pb = q_ob + al(N * 16), q_fb = q_pb + al(N * 4), q_ab = q_fb + al(T * 8), out_total = q_ab + 256;
+                 q_pb = q_ob + al(N * 16), q_fb = q_pb + al(N * 4), q_ab = q_fb + al(T * 8), q_mask = q_ab + 256,
+                 out_total = q_mask + al((size_t)mask_words * 4) + 256;
     rc = g_out.ensure(out_total, device);
     if (rc) return cuda_fail(rc, "cudaMalloc(outputs)");
     char* dout = (char*)g_out.p;
     if (want_bwd) {
-        rc = d2d_power_bwd(&dp, Zbar ? (const float*)(din + o_zbar) : nullptr, Z ? (float*)(dout + q_z) : nullptr,
+        // value, then the VJP over the paths the forward found alive (the activity mask is the only residual)
+        dp.active_mask = (uint32_t*)(dout + q_mask);
+        rc = d2d_power_fwd(&dp, (float*)(dout + q_z), nullptr, s);
+        if (rc != D2D_OK) return rc;
+        rc = d2d_power_bwd(&dp, Zbar ? (const float*)(din + o_zbar) : nullptr, nullptr,
                            grid_bar ? (float*)(dout + q_gb) : nullptr, objects_bar ? (float*)(dout + q_ob) : nullptr,
                            phis_bar ? (float*)(dout + q_pb) : nullptr, fixed_bar ? (float*)(dout + q_fb) : nullptr,
                            alpha_bar ? (float*)(dout + q_ab) : nullptr, s);

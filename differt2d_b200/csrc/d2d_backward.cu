@@ -312,12 +312,13 @@ struct BwdAcc {
 template <int MODE, int METHOD, int K, bool TXGRID>
 __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
                                               const float alpha, const float2 fx, const float2 g, const long long col0,
-                                              int& buf, const float zbar, BwdAcc& A, float* s_obj, float* s_phi) {
+                                              int& buf, const float zbar, BwdAcc& A, float* s_obj, float* s_phi,
+                                              const uint32_t* mread) {
     constexpr int KK = K > 0 ? K : 1;
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
     for_each_candidate<MODE, METHOD, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
+        T, p, tile, sh, alpha, fx, col0, mread, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
             bool has = false;
             float2 txb = make_float2(0.f, 0.f), rxb = make_float2(0.f, 0.f);
             float ab = 0.f;
@@ -413,6 +414,9 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
         const float2 fx = reinterpret_cast<const float2*>(p.fixed)[t];
         float zbar = 0.f;
         if (active) zbar = Zbar ? Zbar[p.reduce_all ? r : (long long)t * p.R + r] : 1.0f;
+        const uint32_t* mread =
+            p.mask ? p.mask + ((long long)t * gridDim.x * (kBlock / 32) + (long long)blockIdx.x * (kBlock / 32)) * p.mask_wpw
+                   : nullptr;
         BwdAcc A;
         A.grid_bar = A.fixed_bar = make_float2(0.f, 0.f);
         A.alpha_bar = 0.f;
@@ -420,11 +424,11 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
         long long col0 = 0;
         for (int k = p.min_order; k <= p.max_order; ++k) {
             switch (k) {
-                case 0: run_order_bwd<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 1: run_order_bwd<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 2: run_order_bwd<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 3: run_order_bwd<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
-                case 4: run_order_bwd<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi); break;
+                case 0: run_order_bwd<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 1: run_order_bwd<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 2: run_order_bwd<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 3: run_order_bwd<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 4: run_order_bwd<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
                 default: break;
             }
             col0 += order_count(k, T.n_allowed);

@@ -58,6 +58,10 @@ struct KParams {
     float h2;                      // (float)(height*height), folded in double like Python does
     float rc_pow[kMaxOrder + 1];   // (float)(r_coef**k)
     uint32_t blocked[D2D_MAX_OBJECTS / 32];  // bit j set: object j is never visited (filter_objects)
+    // activity mask (optional): bit (t, warp, candidate column) = "some lane of the warp has validity != 0".
+    // The forward kernel writes it, the backward kernel then only re-traces the set bits (no cull, no dead paths).
+    uint32_t* mask;            // [T, gridDim.x * 4 warps, mask_wpw] words, or nullptr
+    long long mask_wpw;        // words per (fixed point, warp) = ceil(C_total / 32)
 };
 
 // ---- shared-memory scene table ---------------------------------------------------------------

@@ -301,10 +301,14 @@ __device__ __forceinline__ long long order_count(const int K, const int m) {
 // WARP — for every candidate that survives the tile and warp culls, in list order.  `col0` = column of the first
 // candidate of this order in the global list; `apex` = image of fx through the candidate's objects (ImagePath on a
 // receivers grid only, otherwise unspecified).
+// `mread` (backward kernel after a forward that wrote the activity mask): rows of this CTA's four warps for the
+// current fixed point; the stored bits then REPLACE both culls — only candidates some warp of the CTA found
+// valid are decoded, and each warp only visits its own set bits.
 template <int MODE, int METHOD, int K, bool TXGRID, class Visit>
 __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KParams& p, const Tile& tile,
                                                    DriverShared& sh, const float alpha, const float2 fx,
-                                                   const long long col0, int& buf, Visit&& visit) {
+                                                   const long long col0, const uint32_t* __restrict__ mread, int& buf,
+                                                   Visit&& visit) {
     const int m = T.n_allowed;
     const long long Ck = order_count(K, m);
     if (Ck == 0) return;
@@ -316,7 +320,8 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     }
     constexpr int KK = K > 0 ? K : 1;
     constexpr bool kApex = (METHOD == D2D_METHOD_IMAGE) && !TXGRID;
-    const bool cull = kApex && p.cull;
+    const bool cull = kApex && p.cull && !mread;
+    const long long wpw = p.mask_wpw;
     const float xz = x_zero<MODE>(alpha);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     // candidate slices (point-to-point links with huge candidate lists): CTA y walks chunks y, y + slices, ...
@@ -328,7 +333,13 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
         int c[KK];
 #pragma unroll
         for (int i = 0; i < KK; ++i) c[i] = 0;
-        if (idx < Ck) {
+        bool pre = idx < Ck;
+        if (pre && mread) {
+            const long long wd = (col0 + idx) >> 5;
+            const uint32_t any4 = mread[wd] | mread[wpw + wd] | mread[2 * wpw + wd] | mread[3 * wpw + wd];
+            pre = (any4 >> ((col0 + idx) & 31)) & 1u;
+        }
+        if (pre) {
             // index -> positions in `allowed` (lexicographic, no equal neighbours)
             long long rem = idx;
             int dig[KK];
@@ -379,7 +390,15 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
         for (int q0 = 0; q0 < n3; q0 += 32) {
             const int nq = min(32, n3 - q0);
             unsigned todo = nq >= 32 ? 0xffffffffu : ((1u << nq) - 1u);
-            if (cull) {  // warp-level refinement: lane q tests survivor q0 + q against this warp's box
+            if (mread) {  // this warp's own bits
+                bool wk = false;
+                if (lane < nq) {
+                    const int4 e = sh.list[buf][slot_of(q0 + lane)];
+                    const long long col = col0 + (((long long)(unsigned)e.z) | ((long long)e.w << 32));
+                    wk = (mread[warp * wpw + (col >> 5)] >> (col & 31)) & 1u;
+                }
+                todo = __ballot_sync(0xffffffffu, wk);
+            } else if (cull) {  // warp-level refinement: lane q tests survivor q0 + q against this warp's box
                 bool wk = false;
                 if (lane < nq && tile.wbox.x <= tile.wbox.z) {  // (a warp without active points skips everything)
                     const int sl = slot_of(q0 + lane);

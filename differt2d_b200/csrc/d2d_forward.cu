@@ -15,29 +15,34 @@ namespace d2d {
 template <int MODE, int METHOD, int K, bool TXGRID>
 __device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
                                           const float alpha, const float2 fx, const float2 g, const long long col0,
-                                          int& buf, float& acc, float* vrow) {
+                                          int& buf, float& acc, float* vrow, uint32_t* mrow) {
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
     for_each_candidate<MODE, METHOD, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
-            if (!tile.active) return;
+        T, p, tile, sh, alpha, fx, col0, nullptr, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
             float2 X[K + 2];
-            float valid;
-            if constexpr (METHOD == D2D_METHOD_IMAGE) {
-                // construction fused with on_objects: most paths that reach this point die at their last interaction
-                float onx;
-                const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
-                if (!image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx)) return;
-                valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
-            } else {
-                float loss;
-                construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-                valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+            float valid = 0.0f;
+            if (tile.active) {
+                if constexpr (METHOD == D2D_METHOD_IMAGE) {
+                    // construction fused with on_objects: most paths that reach this point die at an interaction
+                    float onx;
+                    const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
+                    if (image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx))
+                        valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
+                } else {
+                    float loss;
+                    construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
+                    valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+                }
+                if (valid != 0.0f) {
+                    float r;
+                    acc = acc + valid * path_value<K>(p, X, r);  // scene.py:1909
+                    if (vrow) vrow[col] = valid;                 // (valid_out is zero-filled by the launcher)
+                }
             }
-            if (valid != 0.0f) {
-                float r;
-                acc = acc + valid * path_value<K>(p, X, r);  // scene.py:1909
-                if (vrow) vrow[col] = valid;                 // (valid_out is zero-filled by the launcher)
+            if (mrow) {  // activity bit of (this warp, candidate) for the backward kernel; zero-filled by the launcher
+                if (__any_sync(0xffffffffu, valid != 0.0f) && (threadIdx.x & 31) == 0)
+                    atomicOr(&mrow[col >> 5], 1u << (col & 31));
             }
         });
 }
@@ -59,13 +64,16 @@ __global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(con
         float acc = 0.0f;  // scene.py:1893
         long long col0 = 0;
         float* vrow = (valid_out && tile.active) ? valid_out + ((long long)t * p.R + tile.r) * p.C_total : nullptr;
+        uint32_t* mrow = p.mask ? p.mask + ((long long)t * gridDim.x * (kBlock / 32) + (long long)blockIdx.x * (kBlock / 32) +
+                                            (threadIdx.x >> 5)) * p.mask_wpw
+                                : nullptr;
         for (int k = p.min_order; k <= p.max_order; ++k) {
             switch (k) {
-                case 0: run_order<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
-                case 1: run_order<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
-                case 2: run_order<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
-                case 3: run_order<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
-                case 4: run_order<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow); break;
+                case 0: run_order<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 1: run_order<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 2: run_order<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 3: run_order<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 4: run_order<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
                 default: break;
             }
             col0 += order_count(k, T.n_allowed);
@@ -134,6 +142,11 @@ int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, floa
     }
     if (valid_out) {
         const cudaError_t e = cudaMemsetAsync(valid_out, 0, sizeof(float) * (size_t)p.T * p.R * p.C_total, stream);
+        if (e != cudaSuccess) return (int)e;
+    }
+    if (p.mask) {
+        const size_t words = (size_t)p.T * (size_t)host_tile_blocks(p) * (kBlock / 32) * (size_t)p.mask_wpw;
+        const cudaError_t e = cudaMemsetAsync(p.mask, 0, sizeof(uint32_t) * words, stream);
         if (e != cudaSuccess) return (int)e;
     }
     int e;

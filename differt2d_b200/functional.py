@@ -73,6 +73,7 @@ class _Packed:
         self.fixed = _dev_f32(fixed, device).reshape(-1, 2)
         self.grid = _dev_f32(grid, device).reshape(-1, 2)
         self.x0 = None if x0 is None else _dev_f32(x0, device)
+        self.mask = None
         self.alpha_t = None
         alpha_f = DEFAULT_ALPHA
         if isinstance(alpha, torch.Tensor):
@@ -124,14 +125,36 @@ class _Packed:
     def z_shape(self):
         return (self.R,) if self.cfg.reduce_all else (self.T, self.R)
 
+    def new_mask(self) -> torch.Tensor:
+        """Device buffer for the activity mask (the only residual the backward can use), attached to the problem."""
+        n = L.lib().d2d_active_mask_words(C.byref(self.p))
+        if n < 0:
+            raise L.D2DError("invalid problem: " + L.lib().d2d_last_error().decode())
+        mask = torch.empty(max(int(n), 1), dtype=torch.int32, device=self.device)
+        self.attach_mask(mask)
+        return mask
+
+    def attach_mask(self, mask: Optional[torch.Tensor]) -> None:
+        if mask is None:
+            self.p.active_mask = None
+            return
+        n = L.lib().d2d_active_mask_words(C.byref(self.p))
+        same_dev = mask.device.type == "cuda" and (
+            self.device.index is None or mask.device.index is None or mask.device.index == self.device.index)
+        if mask.dtype != torch.int32 or not same_dev or mask.numel() < n or not mask.is_contiguous():
+            raise L.D2DError(f"activity mask must be a contiguous int32 tensor of >= {n} words on {self.device}")
+        self.mask = mask
+        self.p.active_mask = mask.data_ptr()
+
 
 def _stream(device) -> int:
     return torch.cuda.current_stream(device).cuda_stream
 
 
 def power_fwd(cfg: TraceConfig, xys, fixed, grid, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA, x0=None,
-              want_valid: bool = False, device=None):
-    """Z [T,R] (or [R]); with want_valid also the validity of every (fixed, grid point, candidate)."""
+              want_valid: bool = False, want_mask: bool = False, device=None):
+    """Z [T,R] (or [R]); with want_valid also the validity of every (fixed, grid point, candidate); with want_mask
+    also the activity mask to hand to power_bwd(mask=...) for the same inputs (returned last)."""
     device = torch.device(device) if device is not None else (
         grid.device if isinstance(grid, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
     pk = _Packed(cfg, xys, kinds, phis, fixed, grid, alpha, x0, device)
@@ -140,17 +163,23 @@ def power_fwd(cfg: TraceConfig, xys, fixed, grid, *, kinds=None, phis=None, alph
         valid = None
         if want_valid:
             valid = torch.empty((pk.T, pk.R, pk.num_candidates), dtype=torch.float32, device=device)
+        mask = pk.new_mask() if want_mask else None
         rc = L.lib().d2d_power_fwd(C.byref(pk.p), Z.data_ptr(), valid.data_ptr() if want_valid else None, _stream(device))
         L.check(rc, "d2d_power_fwd")
-    return (Z, valid) if want_valid else Z
+    out = (Z,) + ((valid,) if want_valid else ()) + ((mask,) if want_mask else ())
+    return out if len(out) > 1 else Z
 
 
 def power_bwd(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA, x0=None,
-              want=("Z", "grid", "objects", "phis", "fixed", "alpha"), device=None) -> dict:
-    """Recompute-based VJP; returns a dict with the requested cotangents (and Z for value_and_grad)."""
+              want=("Z", "grid", "objects", "phis", "fixed", "alpha"), mask: Optional[torch.Tensor] = None,
+              device=None) -> dict:
+    """Recompute-based VJP; returns a dict with the requested cotangents (and Z for value_and_grad).  ``mask``: the
+    activity mask a power_fwd(want_mask=True) over the SAME inputs returned; the kernel then re-traces only the
+    paths the forward found alive (identical results)."""
     device = torch.device(device) if device is not None else (
         grid.device if isinstance(grid, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
     pk = _Packed(cfg, xys, kinds, phis, fixed, grid, alpha, x0, device)
+    pk.attach_mask(mask)
     with torch.cuda.device(device):
         zb = None
         if Zbar is not None:
@@ -175,29 +204,54 @@ def power_bwd(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis
     return out
 
 
+def power_value_and_vjp(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA,
+                        x0=None, want=("grid", "objects", "phis", "fixed", "alpha"), device=None) -> dict:
+    """Z and the requested cotangents (what jax.value_and_grad / jax.vjp deliver): the forward kernel, then the
+    backward kernel over the paths the forward found alive (activity mask).  Returns the dict of power_bwd + "Z"."""
+    device = torch.device(device) if device is not None else (
+        grid.device if isinstance(grid, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
+    Z, mask = power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, want_mask=True, device=device)
+    out = power_bwd(cfg, xys, fixed, grid, Zbar, kinds=kinds, phis=phis, alpha=alpha, x0=x0,
+                    want=tuple(w for w in want if w != "Z"), mask=mask, device=device)
+    out["Z"] = Z
+    return out
+
+
 class _PowerMap(torch.autograd.Function):
     """custom_vjp analogue: residuals are the inputs only; the backward re-traces (no stored activations)."""
 
     @staticmethod
     def forward(ctx, xys, phis, fixed, grid, alpha, cfg, kinds, x0):
         ctx.cfg, ctx.kinds, ctx.x0 = cfg, kinds, x0
-        ctx.save_for_backward(xys, phis, fixed, grid, alpha)
-        return power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, device=grid.device)
+        need_bwd = any(t.requires_grad for t in (xys, phis, fixed, grid, alpha))
+        if not need_bwd:
+            ctx.save_for_backward(xys, phis, fixed, grid, alpha)
+            ctx.has_mask = False
+            return power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, device=grid.device)
+        # residuals: the inputs and one activity bit per (fixed point, warp, candidate)
+        Z, mask = power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, want_mask=True,
+                            device=grid.device)
+        ctx.save_for_backward(xys, phis, fixed, grid, alpha, mask)
+        ctx.has_mask = True
+        return Z
 
     @staticmethod
     def backward(ctx, Zbar):
-        xys, phis, fixed, grid, alpha = ctx.saved_tensors
+        if ctx.has_mask:
+            xys, phis, fixed, grid, alpha, mask = ctx.saved_tensors
+        else:
+            (xys, phis, fixed, grid, alpha), mask = ctx.saved_tensors, None
         need = ctx.needs_input_grad
         want = [w for w, n in zip(("objects", "phis", "fixed", "grid", "alpha"), need[:5]) if n]
         if ctx.cfg.reduce_all or fixed.shape[0] == 1:
             g = power_bwd(ctx.cfg, xys, fixed, grid, Zbar.contiguous(), kinds=ctx.kinds, phis=phis, alpha=alpha,
-                          x0=ctx.x0, want=tuple(want), device=grid.device)
+                          x0=ctx.x0, want=tuple(want), mask=mask, device=grid.device)
             gg = g.get("grid")
             if gg is not None:
                 gg = gg.reshape(-1, 2) if ctx.cfg.reduce_all else gg.sum(dim=0)
         else:
             g = power_bwd(ctx.cfg, xys, fixed, grid, Zbar.contiguous(), kinds=ctx.kinds, phis=phis, alpha=alpha,
-                          x0=ctx.x0, want=tuple(want), device=grid.device)
+                          x0=ctx.x0, want=tuple(want), mask=mask, device=grid.device)
             gg = g.get("grid")
             if gg is not None:
                 gg = gg.sum(dim=0)

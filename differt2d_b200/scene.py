@@ -280,8 +280,8 @@ class Scene:
             if reduce_all:
                 return back(Z.reshape(shape))
             return ((k, back(Z[i].reshape(shape))) for i, k in enumerate(names))
-        out = F.power_bwd(cfg, xys, fixed, grid, None, kinds=kinds, phis=phis, alpha=alpha, x0=x0,
-                          want=("Z", "grid"), device=device)
+        out = F.power_value_and_vjp(cfg, xys, fixed, grid, None, kinds=kinds, phis=phis, alpha=alpha, x0=x0,
+                                    want=("grid",), device=device)
         Z, dZ = out["Z"], out["grid"]
         if reduce_all:
             Z, dZ = back(Z.reshape(shape)), back(dZ.reshape(*shape, 2))

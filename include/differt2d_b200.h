@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define D2D_ABI_VERSION 1
+#define D2D_ABI_VERSION 2
 
 /* limits of this build */
 #define D2D_MAX_ORDER 4      /* interactions per path (reference examples use <= 3) */
@@ -102,6 +102,12 @@ typedef struct D2DProblem {
     int32_t candidate_slices; /* 0 = automatic.  > 1: that many CTAs share each tile's candidate list and combine  */
                               /* their partial sums with fp32 atomics (point-to-point links with huge lists, e.g.  */
                               /* 500 objects at order 3); the summation order of Z is then not the list order.     */
+    uint32_t *active_mask; /* optional DEVICE buffer of d2d_active_mask_words(p) words: the custom_vjp RESIDUAL.       */
+                           /* d2d_power_fwd fills it with one bit per (fixed point, warp of 32 grid points, candidate):  */
+                           /* "some path of this group has a non-zero validity".  d2d_power_bwd, given the buffer a    */
+                           /* forward over the SAME inputs filled, re-traces only the set bits instead of the whole     */
+                           /* candidate list (identical results; the reference keeps a full tape of every intermediate */
+                           /* at [n,m] size instead, scene.py:1920-1952).  NULL: the backward re-traces everything.     */
 } D2DProblem;
 
 /* Fills a problem with the reference's defaults (defaults.py, geometry.py:915, optimize.py:49,83). */
@@ -119,6 +125,8 @@ int d2d_candidates_device(int32_t n_objects, int32_t order, const int32_t *filte
                           int32_t n_filter, int32_t *out /*device*/, void *stream);
 /* Total over [min_order, max_order] as used by a problem (= columns of `valid_out`). */
 int64_t d2d_problem_num_candidates(const D2DProblem *p);
+/* Size, in 32-bit words, of the `active_mask` residual of a problem; -1 on invalid arguments. */
+int64_t d2d_active_mask_words(const D2DProblem *p);
 
 /*
  * Forward map.  Z: [n_fixed, R] (or [R] when reduce_all), Z[t,r] = sum over candidates, in list

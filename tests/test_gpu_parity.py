@@ -531,6 +531,60 @@ def test_solver_autograd_function():
     assert torch.allclose(xy_t.grad, ref["objects"], rtol=1e-3, atol=1e-3 * ref["objects"].abs().max().item())
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("case", ["geojson", "geojson_norm_flat", "multi_tx_txgrid", "fermat", "slices"])
+def test_activity_mask_backward_equals_full_retrace(mode, case):
+    """The backward kernel driven by the forward's activity mask (the custom_vjp residual) must return exactly what
+    the full re-trace returns: per-receiver outputs bit for bit, scene-parameter cotangents up to the order of
+    their fp32 atomics."""
+    kw, extra = dict(max_order=2), {}
+    if case == "geojson":
+        sc, n, m = SCENES["geojson"], 96, 112
+        kw.update(grid_cols=m)
+    elif case == "geojson_norm_flat":
+        sc, n, m = SCENES["geojson_norm"], 50, 70  # 1-D tiles, ragged last CTA
+    elif case == "multi_tx_txgrid":
+        sc, n, m = SCENES["basic"], 40, 48
+        sc = d.Scene(sc.transmitters, {"rx": d.Point(xy=[0.3, 0.1]), "rx2": d.Point(xy=[0.7, 0.6])}, sc.objects)
+        kw.update(grid_role="transmitters", grid_cols=m)
+    elif case == "fermat":
+        sc, n, m = _vertex_scene(), 12, 16
+        kw.update(method="fermat", steps=20, grid_cols=m)
+        extra["x0"] = np.random.default_rng(1234).random((50, 2), dtype=np.float32)
+    else:
+        sc, n, m = SCENES["geojson_norm"], 4, 2
+        kw.update(min_order=1, max_order=3, candidate_slices=5)
+    X, Y = H.jittered_grid(sc, n, m, seed=9)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, kinds, phis = sc.packed_objects()
+    src = sc.receivers if kw.get("grid_role") == "transmitters" else sc.transmitters
+    fixed = np.stack([p.xy for p in src.values()])
+    for reduce_all in (False, True):
+        cfg = _cfg(mode, reduce_all=reduce_all, **kw)
+        Zbar = (0.5 + np.random.default_rng(3).random((grid.shape[0],) if reduce_all else (fixed.shape[0], grid.shape[0]))
+                ).astype(np.float32)
+        full = F.power_bwd(cfg, xys, fixed, grid, Zbar, kinds=kinds, phis=phis, alpha=50.0, device="cuda", **extra)
+        Z, mask = F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=50.0, want_mask=True, device="cuda",
+                              **extra)
+        got = F.power_bwd(cfg, xys, fixed, grid, Zbar, kinds=kinds, phis=phis, alpha=50.0, mask=mask, device="cuda",
+                          **extra)
+        if case != "slices":  # (8 points at orders 2-3: hard logic may leave no path alive at all)
+            assert int(mask.ne(0).sum()) > 0
+        if case != "slices":  # (slices combine partial sums with atomics: summation order differs run to run)
+            assert torch.equal(Z, full["Z"]) and torch.equal(got["Z"], full["Z"]), (mode, case, reduce_all)
+            assert torch.equal(got["grid"], full["grid"]), (mode, case, reduce_all)
+        else:
+            assert torch.allclose(got["Z"], full["Z"], rtol=1e-5, atol=1e-6 * float(full["Z"].abs().max()))
+            assert torch.allclose(got["grid"], full["grid"], rtol=1e-4, atol=1e-5 * float(full["grid"].abs().max()))
+        for k in ("objects", "phis", "fixed", "alpha"):
+            scale = max(float(full[k].abs().max()), 1e-30)
+            assert torch.allclose(got[k], full[k], rtol=1e-4, atol=1e-5 * scale), (mode, case, reduce_all, k)
+        both = F.power_value_and_vjp(cfg, xys, fixed, grid, Zbar, kinds=kinds, phis=phis, alpha=50.0, device="cuda",
+                                     **extra)
+        if case != "slices":
+            assert torch.equal(both["Z"], full["Z"]) and torch.equal(both["grid"], full["grid"])
+
+
 def test_scene_api_solver_methods():
     sc = _vertex_scene()
     X, Y = sc.grid(24, 20)
