@@ -189,6 +189,12 @@ __device__ __forceinline__ float rcp_approx(float x) {
     return r;
 }
 
+__device__ __forceinline__ float sqrt_approx(float x) {
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // Wall.image_of — geometry.py:652-670
 __device__ __forceinline__ float2 mirror(const float2 p, const float4 w0, const float4 w1) {
     const float ix = p.x - w0.x, iy = p.y - w0.y;

@@ -160,9 +160,16 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
     bool all_walls = true, any_deg = false;
     bool g_out = false, lens_ok = true;
     bool deg_pending = false, deg_dead = false;
-#pragma unroll
+    // The stage loop and the corner loop are ROLLED on purpose: these kernels are instruction-fetch bound
+    // (profiles/), and the unrolled form made the cull a 24 KB straight line that every warp streamed through
+    // once per candidate.  c[i] / I[i+1] are picked with selects so that the arrays stay in registers.
+#pragma unroll 1
     for (int i = K - 1; i >= 0; --i) {
-        const int j = c[i];
+        int j = c[0];
+        float2 A = I[1];
+#pragma unroll
+        for (int u = 1; u < K; ++u)
+            if (i == u) { j = c[u]; A = I[u + 1]; }
         const float4 w0 = T.w0[j];
         const float4 w1 = T.w1[j];
         const int kind = T.kind[j];
@@ -174,12 +181,10 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
             // s = 0 passes on_objects iff act(0) != 0, i.e. xz < 0 (hard: 0 >= 0 is true)
             continue;
         }
-        const float2 A = I[i + 1];
         float smin = CUDART_INF_F, smax = -CUDART_INF_F, gmin = CUDART_INF_F, gmax = -CUDART_INF_F;
         float unmin = CUDART_INF_F, U1 = 0.f, V1 = 0.f, uxm = 0.f, uym = 0.f, u2m = 0.f;
         int pos = 0, neg = 0;
-        // rolled on purpose: these kernels are instruction-fetch bound (profiles/), and the unrolled corner loop
-        // made the cull a 24 KB straight line that every warp streamed through once per candidate
+        const float rtt = rcp_approx(w1.z);
 #pragma unroll 1
         for (int q = 0; q < npts; ++q) {
             const float2 pq = q == 0 ? pts[0] : (q == 1 ? pts[1] : (q == 2 ? pts[2] : pts[3]));
@@ -189,35 +194,38 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
             const float vn = fmaf(vx, w1.x, vy * w1.y);
             pos += un > 0.f;
             neg += un < 0.f;
-            const float g = vn / un;
+            // MUFU-based quotients (relative error < 2^-22 = 4 eps): accounted for in xmag and ds below
+            const float g = vn * rcp_approx(un);
             const float Xx = fmaf(g, ux, pq.x), Xy = fmaf(g, uy, pq.y);
-            const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) / w1.z;
+            const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) * rtt;
             smin = fminf(smin, s); smax = fmaxf(smax, s);
             gmin = fminf(gmin, g); gmax = fmaxf(gmax, g);
             unmin = fminf(unmin, fabsf(un));
             U1 = fmaxf(U1, fabsf(ux) + fabsf(uy));
             V1 = fmaxf(V1, fabsf(vx) + fabsf(vy));
             uxm = fmaxf(uxm, fabsf(ux)); uym = fmaxf(uym, fabsf(uy));
-            u2m = fmaxf(u2m, sqrtf(fmaf(ux, ux, uy * uy)));
+            u2m = fmaxf(u2m, fmaf(ux, ux, uy * uy));
         }
+        u2m = sqrt_approx(u2m) * 1.000001f;  // max |u| over the point set, rounded up
         if (!(pos == npts || neg == npts)) return true;            // u.n may vanish inside the set
         if (!(smin == smin) || !(smax == smax) || !(gmin == gmin) || !(gmax == gmax)) return true;
         if (!(unmin > 64.0f * eps * U1 + 4.0f * dev)) return true;  // u.n not reliably away from zero
-        const float gabs = fmaxf(fabsf(gmin), fabsf(gmax));
-        const float lip = (1.0f + gabs) * (1.0f + u2m / unmin);
-        const float amp = 4.4f * (V1 + gabs * U1) / unmin;
-        const float xmag = S + gabs * u2m;
+        const float gabs = fmaxf(fabsf(gmin), fabsf(gmax)) * 1.000001f;
+        const float run = rcp_approx(unmin) * 1.000001f;  // 1 / min |u.n|, rounded up
+        const float lip = (1.0f + gabs) * (1.0f + u2m * run);
+        const float amp = 4.4f * (V1 + gabs * U1) * run;
+        const float xmag = S + 5.0f * gabs * u2m;  // (4 of the 5: the approximate quotient g at the extreme points)
         const float dXx = eps * (xmag + 4.0f * gabs * uxm + amp * uxm) + 1.5f * lip * dev;
         const float dXy = eps * (xmag + 4.0f * gabs * uym + amp * uym) + 1.5f * lip * dev;
         const float smag = fmaxf(fabsf(smin), fabsf(smax));
-        const float ds = (fabsf(w0.z) * dXx + fabsf(w0.w) * dXy) / w1.z + 4.0f * eps * smag;
+        const float ds = (fabsf(w0.z) * dXx + fabsf(w0.w) * dXy) * (rtt * 1.000001f) + 8.0f * eps * smag;
         const float tol = 2.5f * ds + 1e-6f;
         if (!(tol < CUDART_INF_F)) return true;
         if (i == K - 1) tol_last = tol;  // valid for every point of the tile: reused by warp_may_be_valid
         const float lo = xz - tol, hi = 1.0f - xz + tol;
         if (smax < lo || smin > hi) return false;                  // rule (1)
         // g-range and segment lengths for rules (2) and (3)
-        const float dg = 1.5f * dev * (1.0f + gabs) / unmin + 8.0f * eps * (gabs + (V1 + gabs * U1) / unmin);
+        const float dg = 1.5f * dev * (1.0f + gabs) * run + 12.0f * eps * (gabs + (V1 + gabs * U1) * run);
         const float glo = gmin - dg, ghi = gmax + dg;
         if (ghi < -1.0f || glo > 0.0f) g_out = true;
         const float g_abs_min = glo > 0.0f ? glo : (ghi < 0.0f ? -ghi : 0.0f);
