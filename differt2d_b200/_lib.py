@@ -11,7 +11,8 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "_lib", "libdiffert2d_b200.so")
+# D2D_B200_LIB selects another build of the SAME library (diagnostic builds with cull counters); never a fallback
+LIB_PATH = os.environ.get("D2D_B200_LIB") or os.path.join(HERE, "_lib", "libdiffert2d_b200.so")
 
 MAX_ORDER = 4
 MAX_OBJECTS = 1024

@@ -54,17 +54,25 @@ def needs_build() -> bool:
     return any(os.path.getmtime(f) > t for f in _deps())
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, debug_counters: bool = False) -> str:
+    """debug_counters: diagnostic library libdiffert2d_b200_dbg.so (forward units only count; select it at run time
+    with D2D_B200_LIB=<path>); never the default."""
+    if debug_counters:
+        return _build(verbose, ["-DD2D_DEBUG_COUNTERS"], "dbg_", os.path.join(OUT_DIR, "libdiffert2d_b200_dbg.so"))
     if not force and not needs_build():
         return LIB
+    return _build(verbose, [], "", LIB)
+
+
+def _build(verbose: bool, defs, prefix: str, lib_path: str) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     nvcc = _nvcc()
     objs = []
 
     def compile_one(item):
         src, objname, extra = item
-        obj = os.path.join(OUT_DIR, objname)
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, src), "-o", obj]
+        obj = os.path.join(OUT_DIR, prefix + objname)
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
@@ -77,13 +85,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(len(UNITS), os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, UNITS))
-    cmd = [nvcc, *ARCH, "-shared", "-o", LIB, *objs, "--cudart", "static"]
+    cmd = [nvcc, *ARCH, "-shared", "-o", lib_path, *objs, "--cudart", "static"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    return LIB
+    return lib_path
 
 
 if __name__ == "__main__":
-    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv)
+    path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
+                 debug_counters="--debug-counters" in sys.argv)
     print(path)

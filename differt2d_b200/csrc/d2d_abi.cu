@@ -187,6 +187,9 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
 }  // namespace
 
 extern "C" {
+#ifdef D2D_DEBUG_COUNTERS
+int d2d_debug_counters(int32_t mode, uint64_t* out32, int32_t reset);
+#endif
 
 void d2d_problem_defaults(D2DProblem* p) {
     if (!p) return;
@@ -427,6 +430,18 @@ int d2d_fma_peak_launch(float* sink, int32_t iters, double* flops, void* stream)
     const cudaError_t e = cudaGetLastError();
     return e == cudaSuccess ? D2D_OK : cuda_fail(e, "fma_peak_kernel");
 }
+
+#ifdef D2D_DEBUG_COUNTERS
+// diagnostic builds only: census of the forward kernel's culls for one logic mode (reset != 0 clears it)
+int d2d_debug_counters(int32_t mode, uint64_t* out32, int32_t reset) {
+    switch (mode) {
+        case D2D_MODE_HARD: d2d::debug_counters_mode<D2D_MODE_HARD>((unsigned long long*)out32, reset); break;
+        case D2D_MODE_HARD_SIGMOID: d2d::debug_counters_mode<D2D_MODE_HARD_SIGMOID>((unsigned long long*)out32, reset); break;
+        default: d2d::debug_counters_mode<D2D_MODE_SIGMOID>((unsigned long long*)out32, reset); break;
+    }
+    return D2D_OK;
+}
+#endif
 
 const char* d2d_last_error(void) { return g_err.c_str(); }
 int32_t d2d_abi_version(void) { return D2D_ABI_VERSION; }

@@ -37,12 +37,21 @@ constexpr int kBlock = 128;
 constexpr int kTileCols = 16;
 constexpr int kTileRows = 8;
 
+// Optional census of the cull (diagnostic builds only: python -m differt2d_b200.build --debug-counters)
+#ifdef D2D_DEBUG_COUNTERS
+__device__ unsigned long long d2d_dbg[32];
+#define D2D_COUNT(i) atomicAdd(&d2d_dbg[i], 1ULL)
+#else
+#define D2D_COUNT(i) ((void)0)
+#endif
+
 struct Tile {
     long long r;      // grid-point index of this thread (row-major), valid when `active`
     bool active;
     float4 bbox;      // xmin, ymin, xmax, ymax over the tile's active points
     float4 wbox;      // same over this thread's warp (inverted / infinite when the warp has no active point)
     float scale;      // max |coordinate| over tile, fixed points and objects (for error bounds)
+    float scale_x, scale_y;  // the same per component (lon/lat scenes: |x| ~ 5, |y| ~ 50 — the fp32 lattice differs 8x)
 };
 
 struct DriverShared {
@@ -104,14 +113,21 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     xmax = fmaxf(fmaxf(sh.red[0][2], sh.red[1][2]), fmaxf(sh.red[2][2], sh.red[3][2]));
     ymax = fmaxf(fmaxf(sh.red[0][3], sh.red[1][3]), fmaxf(sh.red[2][3], sh.red[3][3]));
     t.bbox = make_float4(xmin, ymin, xmax, ymax);
-    float s = fmaxf(fmaxf(fabsf(xmin), fabsf(xmax)), fmaxf(fabsf(ymin), fabsf(ymax)));
-    if (!(s < CUDART_INF_F)) s = 0.0f;  // empty tile
+    float sx = fmaxf(fabsf(xmin), fabsf(xmax)), sy = fmaxf(fabsf(ymin), fabsf(ymax));
+    if (!(sx < CUDART_INF_F)) sx = 0.0f;  // empty tile
+    if (!(sy < CUDART_INF_F)) sy = 0.0f;
     for (int j = 0; j < p.N; ++j) {    // uniform, N is small next to the candidate count
         const float4 w = T.w0[j];
-        s = fmaxf(s, fmaxf(fmaxf(fabsf(w.x), fabsf(w.y)), fmaxf(fabsf(w.x + w.z), fabsf(w.y + w.w))));
+        sx = fmaxf(sx, fmaxf(fabsf(w.x), fabsf(w.x + w.z)));
+        sy = fmaxf(sy, fmaxf(fabsf(w.y), fabsf(w.y + w.w)));
     }
-    for (int f = 0; f < p.T; ++f) s = fmaxf(s, fmaxf(fabsf(p.fixed[2 * f]), fabsf(p.fixed[2 * f + 1])));
-    t.scale = s;
+    for (int f = 0; f < p.T; ++f) {
+        sx = fmaxf(sx, fabsf(p.fixed[2 * f]));
+        sy = fmaxf(sy, fabsf(p.fixed[2 * f + 1]));
+    }
+    t.scale_x = sx;
+    t.scale_y = sy;
+    t.scale = fmaxf(sx, sy);
     __syncthreads();
     return t;
 }
@@ -146,7 +162,7 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
 template <int K>
 __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (&c)[K > 0 ? K : 1],
                                                   const float2 (&I)[K + 1], const float4 bbox, const float scale,
-                                                  const float xz, const float loss_dead /* tol_loss - xz */,
+                                                  const float scale_x, const float scale_y, const float xz, const float loss_dead /* tol_loss - xz */,
                                                   float& tol_last) {
     tol_last = CUDART_INF_F;
     if (!(xz > -CUDART_INF_F)) return true;
@@ -207,23 +223,24 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
             u2m = fmaxf(u2m, fmaf(ux, ux, uy * uy));
         }
         u2m = sqrt_approx(u2m) * 1.000001f;  // max |u| over the point set, rounded up
-        if (!(pos == npts || neg == npts)) return true;            // u.n may vanish inside the set
-        if (!(smin == smin) || !(smax == smax) || !(gmin == gmin) || !(gmax == gmax)) return true;
-        if (!(unmin > 64.0f * eps * U1 + 4.0f * dev)) return true;  // u.n not reliably away from zero
+        if (!(pos == npts || neg == npts)) { D2D_COUNT(8); return true; }  // u.n may vanish inside the set
+        if (!(smin == smin) || !(smax == smax) || !(gmin == gmin) || !(gmax == gmax)) { D2D_COUNT(9); return true; }
+        if (!(unmin > 64.0f * eps * U1 + 4.0f * dev)) { D2D_COUNT(10); return true; }  // u.n not reliably away from zero
         const float gabs = fmaxf(fabsf(gmin), fabsf(gmax)) * 1.000001f;
         const float run = rcp_approx(unmin) * 1.000001f;  // 1 / min |u.n|, rounded up
         const float lip = (1.0f + gabs) * (1.0f + u2m * run);
         const float amp = 4.4f * (V1 + gabs * U1) * run;
-        const float xmag = S + 5.0f * gabs * u2m;  // (4 of the 5: the approximate quotient g at the extreme points)
-        const float dXx = eps * (xmag + 4.0f * gabs * uxm + amp * uxm) + 1.5f * lip * dev;
-        const float dXy = eps * (xmag + 4.0f * gabs * uym + amp * uym) + 1.5f * lip * dev;
+        const float gu5 = 5.0f * gabs * u2m;  // (4 of the 5: the approximate quotient g at the extreme points)
+        // lattice rounding of X per component: |X_c| <= S_c + |g||u|
+        const float dXx = eps * (scale_x + gu5 + 4.0f * gabs * uxm + amp * uxm) + 1.5f * lip * dev;
+        const float dXy = eps * (scale_y + gu5 + 4.0f * gabs * uym + amp * uym) + 1.5f * lip * dev;
         const float smag = fmaxf(fabsf(smin), fabsf(smax));
         const float ds = (fabsf(w0.z) * dXx + fabsf(w0.w) * dXy) * (rtt * 1.000001f) + 8.0f * eps * smag;
         const float tol = 2.5f * ds + 1e-6f;
         if (!(tol < CUDART_INF_F)) return true;
         if (i == K - 1) tol_last = tol;  // valid for every point of the tile: reused by warp_may_be_valid
         const float lo = xz - tol, hi = 1.0f - xz + tol;
-        if (smax < lo || smin > hi) return false;                  // rule (1)
+        if (smax < lo || smin > hi) { D2D_COUNT(i == K - 1 ? 1 : 2); return false; }  // rule (1)
         // g-range and segment lengths for rules (2) and (3)
         const float dg = 1.5f * dev * (1.0f + gabs) * run + 12.0f * eps * (gabs + (V1 + gabs * U1) * run);
         const float glo = gmin - dg, ghi = gmax + dg;
@@ -247,6 +264,9 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         npts = 2;
         dev = 1.25f * fmaxf(dXx, dXy) + 2.0f * eps * S;
     }
+    // (A direct test of the FIRST interaction through the unfolded path — s_1 over the images of the box corners —
+    // was measured on the bench scenes: it rejected 2 of 100 000 candidates the stage loop had kept, i.e. the
+    // propagated point sets lose nothing there; removed.)
     if (deg_pending) {  // zero-length object(s) right after the transmitter: previous point is tx = I[0]
         float xl = CUDART_INF_F, xh = -CUDART_INF_F, yl = CUDART_INF_F, yh = -CUDART_INF_F;
 #pragma unroll
@@ -261,11 +281,14 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
     }
     if (all_walls) {
         if (any_deg) {
-            if (deg_dead && 0.98f >= loss_dead) return false;       // rule (3)
+            if (deg_dead && 0.98f >= loss_dead) { D2D_COUNT(4); return false; }  // rule (3)
+            D2D_COUNT(7);
         } else if (g_out && lens_ok && 3.9f >= loss_dead) {
+            D2D_COUNT(5);
             return false;                                           // rule (2)
         }
     }
+    D2D_COUNT(6);
     return true;
 }
 
@@ -372,7 +395,11 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
 #pragma unroll
                 for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[c[i]], T.w1[c[i]]);
                 apex = I[K];
-                if (cull) keep = tile_may_be_valid<K>(T, c, I, tile.bbox, tile.scale, xz, p.tol - xz, tol_last);
+                if (cull) {
+                    D2D_COUNT(0);
+                    keep = tile_may_be_valid<K>(T, c, I, tile.bbox, tile.scale, tile.scale_x, tile.scale_y, xz, p.tol - xz,
+                                                tol_last);
+                }
             }
         }
         // ordered compaction: per-warp segments keep list order
@@ -419,6 +446,9 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
                     wk = warp_may_be_valid(T.w0[jl], T.w1[jl], make_float2(a.x, a.y), tile.wbox, a.z, xz);
                 }
                 todo = __ballot_sync(0xffffffffu, wk);
+#ifdef D2D_DEBUG_COUNTERS
+                if (lane == 0) { atomicAdd(&d2d_dbg[13], (unsigned long long)nq); atomicAdd(&d2d_dbg[14], (unsigned long long)__popc(todo)); }
+#endif
             }
 #pragma unroll 1
             while (todo) {

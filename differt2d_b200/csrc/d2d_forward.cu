@@ -27,14 +27,21 @@ __device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, c
                     // construction fused with on_objects: most paths that reach this point die at an interaction
                     float onx;
                     const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
-                    if (image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx))
+                    D2D_COUNT(16);
+                    if (image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx)) {
+                        D2D_COUNT(17);
+                        bool dg = false;
+                        for (int i = 0; i < K; ++i) dg = dg || (T.w0[cd.c[i]].z == 0.f && T.w0[cd.c[i]].w == 0.f);
+                        if (dg) D2D_COUNT(18);
                         valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
+                    }
                 } else {
                     float loss;
                     construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
                     valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
                 }
                 if (valid != 0.0f) {
+                    D2D_COUNT(19);
                     float r;
                     acc = acc + valid * path_value<K>(p, X, r);  // scene.py:1909
                     if (vrow) vrow[col] = valid;                 // (valid_out is zero-filled by the launcher)
@@ -129,6 +136,18 @@ int launch_fwd_mode<D2D_TU_MODE>(const KParams& p, int grid_role, int method, fl
                                  cudaStream_t s) {
     return launch_method<D2D_TU_MODE>(p, grid_role, method, Z, valid_out, s);
 }
+
+#ifdef D2D_DEBUG_COUNTERS
+template <>
+void debug_counters_mode<D2D_TU_MODE>(unsigned long long* out, int reset) {
+    if (reset) {
+        unsigned long long z[32] = {0};
+        cudaMemcpyToSymbol(d2d_dbg, z, sizeof(z));
+    } else {
+        cudaMemcpyFromSymbol(out, d2d_dbg, sizeof(unsigned long long) * 32);
+    }
+}
+#endif
 
 #if D2D_TU_MODE == D2D_MODE_HARD
 long long num_tile_blocks(const KParams& p) { return host_tile_blocks(p); }

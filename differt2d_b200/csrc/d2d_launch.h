@@ -40,4 +40,11 @@ template <> int launch_bwd_mode<D2D_MODE_HARD>(const KParams&, int, int, const f
 template <> int launch_bwd_mode<D2D_MODE_HARD_SIGMOID>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
 template <> int launch_bwd_mode<D2D_MODE_SIGMOID>(const KParams&, int, int, const float*, const BwdOut&, cudaStream_t);
 
+#ifdef D2D_DEBUG_COUNTERS
+template <int MODE> void debug_counters_mode(unsigned long long* out, int reset);
+template <> void debug_counters_mode<D2D_MODE_HARD>(unsigned long long*, int);
+template <> void debug_counters_mode<D2D_MODE_HARD_SIGMOID>(unsigned long long*, int);
+template <> void debug_counters_mode<D2D_MODE_SIGMOID>(unsigned long long*, int);
+#endif
+
 }  // namespace d2d
