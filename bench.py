@@ -38,6 +38,7 @@ GRID_PER_GPU = (1024, 1024)
 MAX_ORDER = 2
 ALPHA = 100.0
 MODE = "hard_sigmoid"
+FLUSH_BYTES = 160 << 20  # > the 126 MB L2
 
 
 def load_scene(coords: str):
@@ -167,7 +168,7 @@ def workload_config(args, world):
                     f"{GRID_PER_GPU[0]}x{GRID_PER_GPU[1]} receivers per GPU",
         "grid_global": [GRID_PER_GPU[0] * world, GRID_PER_GPU[1]],
         "sharding": f"receiver-grid rows over {world} GPU(s); NCCL all-reduce of scene-parameter cotangents",
-        "l2": "L2 flushed between timed steps (256 MiB memset)",
+        "l2": f"L2 flushed between timed steps ({FLUSH_BYTES >> 20} MiB memset, inside the timed region)",
     }
 
 
@@ -272,7 +273,7 @@ def main() -> None:
     base = pbar.data_ptr()
     lib = L.lib()
     stream = torch.cuda.current_stream(dev)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
     def step(i=None):
@@ -382,6 +383,19 @@ def main() -> None:
     for k in kernels.values():
         k["achieved_tflops"] = k["algorithmic_flop"] / (k["ms"] * 1e-3) / 1e12
     dom = max(kernels, key=lambda n: kernels[n]["ms"])
+    # the executed picture of the same command under `ncu --set full` (profiles/, committed; cold-cache capture)
+    ncu = {}
+    try:
+        ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics.json")))["kernels"]
+    except Exception:
+        pass
+    traffic = None
+    executed = None
+    if dom in ncu:
+        traffic = ncu[dom]["dram_bytes_read"] + ncu[dom]["dram_bytes_write"]
+        executed = {k: ncu[dom][k] for k in ("issue_slots_busy_pct", "fp32_lanes_busy_pct", "executed_fp32_flop",
+                                             "warp_instructions", "achieved_occupancy_pct")}
+        executed["source"] = "profiles/ncu_metrics.json (ncu --set full of this command, per launch)"
     algo_bytes = R * (8 + 4 + 4 + 8)  # grid in, Zbar in, Z out... per launch of the dominant kernel
     line = {
         "metric": METRIC, "value": paths_step / (ms_per_step * 1e-3), "unit": UNIT, "n_gpus": world,
@@ -397,10 +411,13 @@ def main() -> None:
         "roofline": {
             "bound": "fp32", "kernel": dom, "achieved": kernels[dom]["achieved_tflops"], "peak": peak_tf,
             "unit": "TFLOP/s", "frac": kernels[dom]["achieved_tflops"] / peak_tf if peak_tf else None,
-            "traffic": None,
+            "traffic": traffic,
+            "executed": executed,
             "peak_source": "FP32 FMA-chain microbenchmark (d2d_fma_peak_launch) timed in this run; "
                            "MEASURED_PEAKS.json holds no FP32 CUDA-core figure",
-            "convention": "ALGORITHMIC flop of SURVEY §8(d) (pruned work still counted; VJP = 2 x forward)",
+            "convention": "ALGORITHMIC flop of SURVEY §8(d) (pruned work still counted; VJP = 2 x forward): exact "
+                          "pruning (tile/warp culls, early outs, activity mask) removes most of it, hence frac > 1; "
+                          "`executed` is what the SMs actually issued",
             "kernels": kernels,
             "hbm": {"algorithmic_bytes_per_launch": algo_bytes,
                     "achieved_gbs": algo_bytes / (kernels[dom]["ms"] * 1e-3) / 1e9,
