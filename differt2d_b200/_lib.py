@@ -64,9 +64,23 @@ class D2DProblem(C.Structure):
     ]
 
 
+class D2DPathRecord(C.Structure):
+    _fields_ = [
+        ("fixed", C.c_int32),
+        ("order", C.c_int32),
+        ("grid", C.c_int64),
+        ("candidate", C.c_int64),
+        ("valid", C.c_float),
+        ("loss", C.c_float),
+        ("value", C.c_float),
+        ("length", C.c_float),
+        ("xys", C.c_float * ((MAX_ORDER + 2) * 2)),
+    ]
+
+
 EXPORTS = [
     "d2d_problem_defaults", "d2d_candidates_count", "d2d_candidates_host", "d2d_candidates_device",
-    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_power_host", "d2d_launch_count",
+    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_paths", "d2d_power_host", "d2d_launch_count",
     "d2d_fma_peak_launch", "d2d_last_error", "d2d_abi_version",
 ]
 
@@ -88,6 +102,8 @@ def lib() -> C.CDLL:
     vp = C.c_void_p
     L.d2d_problem_defaults.argtypes = [P]
     L.d2d_problem_defaults.restype = None
+    L.d2d_paths.argtypes = [P, C.c_float, C.c_int32, vp, C.c_int64, vp, vp]
+    L.d2d_paths.restype = C.c_int
     L.d2d_active_mask_words.argtypes = [P]
     L.d2d_active_mask_words.restype = C.c_int64
     L.d2d_candidates_count.argtypes = [C.c_int32, C.c_int32, vp, C.c_int32]

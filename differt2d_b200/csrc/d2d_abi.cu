@@ -311,6 +311,22 @@ int d2d_power_bwd(const D2DProblem* p, const float* Zbar, float* Z_out, float* g
     return e == 0 ? D2D_OK : cuda_fail(e, "power_bwd_kernel");
 }
 
+int d2d_paths(const D2DProblem* p, float min_valid, int32_t emit_all, D2DPathRecord* records, int64_t capacity,
+              unsigned long long* count, void* stream) {
+    d2d::KParams k;
+    const int rc = pack(p, k);
+    if (rc != D2D_OK) return rc;
+    if (!count) return fail(D2D_ERR_INVALID_ARGUMENT, "count is NULL");
+    if (records && capacity < 0) return fail(D2D_ERR_INVALID_ARGUMENT, "negative capacity");
+    if (p->method != D2D_METHOD_IMAGE && !p->x0 && p->max_order > 0)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "Fermat/MinPath need x0 (initial guesses per candidate)");
+    d2d::PathsOut out{records, records ? (long long)capacity : 0, count, min_valid, emit_all ? 1 : 0};
+    long long n = 0;
+    const int e = d2d::launch_paths(k, p->mode, p->grid_role, p->method, out, (cudaStream_t)stream, &n);
+    g_launches += n;
+    return e == 0 ? D2D_OK : cuda_fail(e, "paths_kernel");
+}
+
 // ---- host-buffer entry ---------------------------------------------------------------------------
 namespace {
 struct DevBuf {

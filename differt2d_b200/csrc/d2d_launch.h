@@ -15,7 +15,22 @@ struct BwdOut {
     float* alpha_bar;    // optional [1]
 };
 
+struct PathsOut {
+    D2DPathRecord* records;  // optional (nullptr: count only)
+    long long capacity;
+    unsigned long long* count;
+    float min_valid;
+    int emit_all;
+};
+
 long long num_tile_blocks(const KParams& p);
+int launch_paths(const KParams& p, int mode, int grid_role, int method, const PathsOut& out, cudaStream_t stream,
+                 long long* launches);
+template <int MODE>
+int launch_paths_mode(const KParams& p, int grid_role, int method, const PathsOut& out, cudaStream_t s);
+template <> int launch_paths_mode<D2D_MODE_HARD>(const KParams&, int, int, const PathsOut&, cudaStream_t);
+template <> int launch_paths_mode<D2D_MODE_HARD_SIGMOID>(const KParams&, int, int, const PathsOut&, cudaStream_t);
+template <> int launch_paths_mode<D2D_MODE_SIGMOID>(const KParams&, int, int, const PathsOut&, cudaStream_t);
 
 // returns cudaError_t as int; *launches incremented by the number of kernels launched
 int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, float* Z, float* valid_out,

@@ -204,6 +204,50 @@ def power_bwd(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis
     return out
 
 
+_REC_WORDS = C.sizeof(L.D2DPathRecord) // 4  # the record as 32-bit words
+
+
+def paths(cfg: TraceConfig, xys, fixed, grid, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA, x0=None,
+          min_valid: float = 0.5, emit_all: bool = False, device=None) -> dict:
+    """
+    Materialised paths — Scene.all_paths (emit_all) / all_valid_paths (valid > min_valid), scene.py:1156-1248 —
+    and the escape hatch for an arbitrary `fun`: one entry per emitted (fixed point, grid point, candidate),
+    sorted by those three indices (= the reference's iteration order).  Returns device tensors
+    fixed i32[n], order i32[n], grid i64[n], candidate i64[n], valid/loss/value/length f32[n],
+    xys f32[n, MAX_ORDER + 2, 2] (rows beyond order + 2 are zero).
+    Two launches of the same kernel: a counting pass sizes the record array, the second fills it.
+    """
+    device = torch.device(device) if device is not None else (
+        grid.device if isinstance(grid, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
+    pk = _Packed(cfg, xys, kinds, phis, fixed, grid, alpha, x0, device)
+    lib = L.lib()
+    with torch.cuda.device(device):
+        count = torch.zeros(1, dtype=torch.int64, device=device)
+        L.check(lib.d2d_paths(C.byref(pk.p), float(min_valid), int(emit_all), None, 0, count.data_ptr(), _stream(device)),
+                "d2d_paths (count)")
+        n = int(count.item())
+        rec = torch.empty((max(n, 1), _REC_WORDS), dtype=torch.int32, device=device)
+        if n:
+            L.check(lib.d2d_paths(C.byref(pk.p), float(min_valid), int(emit_all), rec.data_ptr(), n, count.data_ptr(),
+                                  _stream(device)), "d2d_paths")
+            if int(count.item()) != n:
+                raise L.D2DError("d2d_paths: the two passes disagree on the number of records")
+        rec = rec[:n]
+        i64 = rec[:, 2:6].contiguous().view(torch.int64)
+        f32 = rec[:, 6:].contiguous().view(torch.float32)
+        out = {"fixed": rec[:, 0].contiguous(), "order": rec[:, 1].contiguous(), "grid": i64[:, 0].contiguous(),
+               "candidate": i64[:, 1].contiguous(), "valid": f32[:, 0].contiguous(), "loss": f32[:, 1].contiguous(),
+               "value": f32[:, 2].contiguous(), "length": f32[:, 3].contiguous(),
+               "xys": f32[:, 4:].reshape(n, L.MAX_ORDER + 2, 2).contiguous()}
+        if n:
+            c_total = max(pk.num_candidates, 1)
+            key = (out["fixed"].to(torch.int64) * max(pk.R, 1) + out["grid"]) * c_total + out["candidate"]
+            order = torch.argsort(key)
+            out = {k: v[order] for k, v in out.items()}
+    out["num_candidates"] = pk.num_candidates
+    return out
+
+
 def power_value_and_vjp(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA,
                         x0=None, want=("grid", "objects", "phis", "fixed", "alpha"), device=None) -> dict:
     """Z and the requested cotangents (what jax.value_and_grad / jax.vjp deliver): the forward kernel, then the

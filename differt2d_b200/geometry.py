@@ -97,9 +97,23 @@ class RIS(Wall):
 
 
 class Path:
-    """geometry.py:724-973 — base tag (every object sampled at t = 0.5 in the reference; not fused here)."""
+    """geometry.py:724-973 — a materialised path: ``xys`` [(order + 2), 2] (TX, interaction points, RX) and its
+    ``loss``.  The subclasses double as the TAGS that select the kernels' construction method (``path_cls=``);
+    the base class itself (every object sampled at t = 0.5 in the reference) is not fused."""
 
     METHOD = None
+
+    def __init__(self, xys=None, loss=0.0):
+        self.xys = np.zeros((2, 2), np.float32) if xys is None else np.asarray(xys, dtype=np.float32)
+        self.loss = np.float32(loss)
+
+    def length(self) -> np.float32:
+        """geometry.py:811-819 / path_length :176-203 (eps added to every segment vector, fp32)."""
+        d = (self.xys[1:] - self.xys[:-1]) + np.float32(1.1920929e-07)
+        return np.float32(np.sqrt((d * d).sum(-1, dtype=np.float32)).sum(dtype=np.float32))
+
+    def __repr__(self):
+        return f"{type(self).__name__}(xys={self.xys.tolist()}, loss={float(self.loss):.3g})"
 
 
 class ImagePath(Path):
@@ -118,3 +132,16 @@ class MinPath(Path):
     """geometry.py:1207-1288"""
 
     METHOD = "minpath"
+
+
+class PathBatch:
+    """What a generic `fun` receives from the accumulate_* entry points: all emitted paths of ONE order as device
+    tensors (the batched counterpart of the reference's per-path call ``fun(path, *fun_args, **fun_kwargs)``,
+    scene.py:1909).  ``xys`` f32[n, order + 2, 2]; ``valid`` / ``loss`` f32[n]; ``order`` int."""
+
+    def __init__(self, xys, valid, loss, order):
+        self.xys, self.valid, self.loss, self.order = xys, valid, loss, int(order)
+
+    def length(self):
+        d = (self.xys[:, 1:] - self.xys[:, :-1]) + 1.1920929e-07
+        return d.square().sum(-1).sqrt().sum(-1)

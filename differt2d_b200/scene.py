@@ -23,13 +23,14 @@ import torch
 from . import functional as F
 from . import utils
 from .defaults import DEFAULT_ALPHA, DEFAULT_HEIGHT, DEFAULT_PATCH, DEFAULT_R_COEF
-from .geometry import RIS, FermatPath, ImagePath, MinPath, Path, Point, Vertex, Wall
+from .geometry import RIS, FermatPath, ImagePath, MinPath, Path, PathBatch, Point, Vertex, Wall
 from .logic import resolve_mode
 
 
 def _resolve_fun(fun, fun_args, fun_kwargs):
     fun_kwargs = dict(fun_kwargs or {})
-    if fun_args:
+    fused = fun in (utils.received_power, utils.length_squared, "received_power", "length_squared")
+    if fun_args and fused:
         raise NotImplementedError("positional fun_args are not supported by the fused kernels; use fun_kwargs")
     if fun is utils.received_power or fun == "received_power":
         r_coef = float(fun_kwargs.pop("r_coef", DEFAULT_R_COEF))
@@ -39,10 +40,11 @@ def _resolve_fun(fun, fun_args, fun_kwargs):
         return "received_power", r_coef, height
     if fun is utils.length_squared or fun == "length_squared":
         return "length_squared", DEFAULT_R_COEF, DEFAULT_HEIGHT
-    raise NotImplementedError(
-        "the fused kernels implement fun in {utils.received_power, utils.length_squared}; an arbitrary "
-        "Python `fun` (scene.py:51) needs the generic escape hatch listed under DESIGN.md 'next'"
-    )
+    if callable(fun):
+        # escape hatch: the paths are materialised by the CUDA kernel and `fun` runs in the host framework on the
+        # batched vertices (PathBatch), see Scene._generic_accumulate
+        return "generic", DEFAULT_R_COEF, DEFAULT_HEIGHT
+    raise NotImplementedError("fun must be utils.received_power, utils.length_squared or a callable on PathBatch")
 
 
 def _default_device():
@@ -234,9 +236,28 @@ class Scene:
             raise TypeError("ImagePath cannot interact with Vertex objects (geometry.py:1020 expects walls)")
         cfg = F.TraceConfig(grid_role=grid_role, min_order=min_order, max_order=max_order,
                             filter_nodes=self._filter_nodes(filter_objects), method=method, steps=steps, lr=0.1,
-                            mode=mode, tol=tol, patch=patch, fun=fname, r_coef=r_coef, height=height,
-                            reduce_all=bool(reduce_all))
+                            mode=mode, tol=tol, patch=patch, fun="received_power" if fname == "generic" else fname,
+                            r_coef=r_coef, height=height, reduce_all=bool(reduce_all))
+        self._generic = fname == "generic"
         return cfg, alpha
+
+    def _generic_accumulate(self, cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed, grid, alpha, x0, device):
+        """SURVEY §8 f1 — arbitrary `fun`: Z[t, r] = sum_c valid * fun(path) with the paths materialised by
+        `d2d_paths` (every path whose validity is non-zero) and `fun` evaluated on PathBatch tensors, one call per
+        order.  The summation runs in index order per (t, r) up to the reduction order of index_add_."""
+        rec = F.paths(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, min_valid=0.0, device=device)
+        T, R = np.asarray(fixed).reshape(-1, 2).shape[0], grid.shape[0]
+        Z = torch.zeros(T * R, dtype=torch.float32, device=device)
+        for k in range(cfg.min_order, cfg.max_order + 1):
+            sel = rec["order"] == k
+            if not bool(sel.any()):
+                continue
+            batch = PathBatch(rec["xys"][sel][:, : k + 2], rec["valid"][sel], rec["loss"][sel], k)
+            val = torch.as_tensor(fun(batch, *fun_args, **dict(fun_kwargs or {})), dtype=torch.float32, device=device)
+            val = val.expand(batch.valid.shape)
+            Z.index_add_(0, rec["fixed"][sel].to(torch.int64) * R + rec["grid"][sel], batch.valid * val)
+        Z = Z.reshape(T, R)
+        return Z.sum(0) if cfg.reduce_all else Z
 
     def _x0(self, cfg: F.TraceConfig, key, device):
         """Initial guesses per candidate (optimize.py:132); `key` is an int seed or an explicit [C,max_order] table."""
@@ -275,8 +296,14 @@ class Scene:
             cfg = dataclasses.replace(cfg, grid_cols=int(shape[1]))
         back = (lambda t: t.cpu().numpy()) if as_numpy else (lambda t: t.to(Xt.device))
         want_grad = grad or value_and_grad
+        if self._generic and want_grad:
+            raise NotImplementedError("gradients of a generic `fun` are not fused; use received_power / length_squared")
         if not want_grad:
-            Z = F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, device=device)
+            if self._generic:
+                Z = self._generic_accumulate(cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed, grid, alpha, x0,
+                                             device)
+            else:
+                Z = F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, device=device)
             if reduce_all:
                 return back(Z.reshape(shape))
             return ((k, back(Z[i].reshape(shape))) for i, k in enumerate(names))
@@ -310,6 +337,63 @@ class Scene:
         return self._grid_call("transmitters", X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad,
                                path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs)
 
+    def _materialise(self, path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs,
+                     emit_all: bool, min_valid: float = 0.5):
+        cfg, alpha = self._config("receivers", utils.received_power, (), None, False, path_cls, path_cls_kwargs,
+                                  min_order, max_order, order, filter_objects, kwargs)
+        device = _default_device()
+        tx_names, rx_names = list(self.transmitters), list(self.receivers)
+        if not tx_names or not rx_names:
+            return cfg, tx_names, rx_names, None, []
+        fixed = np.stack([self.transmitters[k].xy for k in tx_names])
+        grid = np.stack([self.receivers[k].xy for k in rx_names])
+        xys, kinds, phis = self.packed_objects()
+        rec = F.paths(cfg, xys, fixed, torch.as_tensor(grid).to(device), kinds=kinds, phis=phis, alpha=alpha,
+                      x0=self._x0(cfg, key, device), min_valid=min_valid, emit_all=emit_all, device=device)
+        rec = {k: (v.cpu().numpy() if isinstance(v, torch.Tensor) else v) for k, v in rec.items()}
+        cands = []
+        for k in range(cfg.min_order, cfg.max_order + 1):
+            cands.extend(list(F.candidates(len(self.objects), k, cfg.filter_nodes)))
+        return cfg, tx_names, rx_names, rec, cands
+
+    def all_paths(self, path_cls: type = ImagePath, path_cls_kwargs=None, min_order: int = 0, max_order: int = 1,
+                  order: Optional[int] = None, filter_objects=None, *, key=None, **kwargs: Any
+                  ) -> Iterator[tuple]:
+        """scene.py:1156-1217 — (tx name, rx name, valid, path, path_candidate) for EVERY candidate of every
+        transmitter-receiver pair, pairs in dictionary order, candidates in list order.  The paths are built and
+        validated by the CUDA kernel (`d2d_paths`, emit_all); ``valid`` is a bool (hard logic) or a float32.
+        NB the reference draws one PRNG key per (pair, candidate) (:1209-1212); this mirror uses the
+        per-candidate x0 table of the grid methods for every pair."""
+        cfg, tx_names, rx_names, rec, cands = self._materialise(path_cls, path_cls_kwargs, min_order, max_order, order,
+                                                                filter_objects, key, dict(kwargs), emit_all=True)
+        if rec is None:
+            return
+        hard = cfg.mode == "hard"
+        for i in range(rec["fixed"].shape[0]):
+            k = int(rec["order"][i])
+            valid = bool(rec["valid"][i] != 0) if hard else np.float32(rec["valid"][i])
+            yield (tx_names[int(rec["fixed"][i])], rx_names[int(rec["grid"][i])], valid,
+                   path_cls(xys=rec["xys"][i, : k + 2].copy(), loss=rec["loss"][i]), cands[int(rec["candidate"][i])])
+
+    def all_valid_paths(self, approx: Optional[bool] = None, **kwargs: Any) -> Iterator[tuple]:
+        """scene.py:1219-1248 — the paths of all_paths for which logic.is_true(valid) holds (valid > 0.5 with
+        approximation, valid itself otherwise, logic.py:542-563), as (tx name, rx name, path, path_candidate).
+        Only those paths leave the GPU (compacted by the kernel)."""
+        path_cls = kwargs.pop("path_cls", ImagePath)
+        kw = dict(approx=approx, **{k: kwargs.pop(k) for k in list(kwargs) if k in ("alpha", "function", "tol", "patch")})
+        cfg, tx_names, rx_names, rec, cands = self._materialise(
+            path_cls, kwargs.pop("path_cls_kwargs", None), kwargs.pop("min_order", 0), kwargs.pop("max_order", 1),
+            kwargs.pop("order", None), kwargs.pop("filter_objects", None), kwargs.pop("key", None), kw, emit_all=False,
+            min_valid=0.5)
+        if kwargs:
+            raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
+        if rec is None:
+            return
+        for i in range(rec["fixed"].shape[0]):
+            k = int(rec["order"][i])
+            yield (tx_names[int(rec["fixed"][i])], rx_names[int(rec["grid"][i])],
+                   path_cls(xys=rec["xys"][i, : k + 2].copy(), loss=rec["loss"][i]), cands[int(rec["candidate"][i])])
+
     def accumulate_over_paths(self, fun=utils.received_power, fun_args: tuple = (),
                               fun_kwargs: Optional[Mapping[str, Any]] = None, *, reduce_all: bool = False,
                               path_cls: type = ImagePath, path_cls_kwargs=None, min_order: int = 0, max_order: int = 1,
@@ -330,8 +414,12 @@ class Scene:
         x0 = self._x0(cfg, key, device)
         if not tx_names or not rx_names:
             return np.float32(0.0) if reduce_all else iter(())
-        Z = F.power_fwd(cfg, xys, fixed, torch.as_tensor(grid), kinds=kinds, phis=phis, alpha=alpha, x0=x0,
-                        device=device).cpu().numpy()
+        if self._generic:
+            Z = self._generic_accumulate(cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed,
+                                         torch.as_tensor(grid).to(device), alpha, x0, device).cpu().numpy()
+        else:
+            Z = F.power_fwd(cfg, xys, fixed, torch.as_tensor(grid), kinds=kinds, phis=phis, alpha=alpha, x0=x0,
+                            device=device).cpu().numpy()
         if reduce_all:
             total = np.float32(0.0)
             for i in range(len(tx_names)):

@@ -149,6 +149,33 @@ int d2d_power_bwd(const D2DProblem *p, const float *Zbar, float *Z_out, float *g
                   void *stream);
 
 /*
+ * Path materialisation — Scene.all_paths / all_valid_paths (scene.py:1156-1248) and the escape hatch for an
+ * arbitrary `fun` evaluated by the host framework on the path vertices.
+ * One record per emitted (fixed point, grid point, candidate), in arrival order (sort by the three indices
+ * for list order).  `xys` holds the order + 2 vertices TX, interaction points..., RX (scene.py's Path.xys).
+ */
+typedef struct D2DPathRecord {
+    int32_t fixed;     /* index into fixed_xy                                                        */
+    int32_t order;     /* number of interactions k                                                   */
+    int64_t grid;      /* index into grid_xy                                                         */
+    int64_t candidate; /* column in the candidate list of the problem (orders ascending, lexicographic) */
+    float valid;       /* Path.is_valid: 0/1 (hard) or the smooth truth value                        */
+    float loss;        /* Path.loss (geometry.py:1077-1084, :1202-1204, :1286-1288)                 */
+    float value;       /* the fused `fun` of the problem (received_power / length**2)                */
+    float length;      /* Path.length() (geometry.py:811-819)                                        */
+    float xys[(D2D_MAX_ORDER + 2) * 2];
+} D2DPathRecord;
+/*
+ * emit_all = 0: records with valid > min_valid only (all_valid_paths: min_valid = 0.5 is logic.is_true's
+ * threshold, logic.py:542-556; hard logic: any min_valid in [0,1)).  emit_all = 1: every triple, as all_paths
+ * yields them (complete path and loss even when invalid; min_valid ignored).
+ * records: DEVICE array of `capacity` records or NULL (count only).  count: DEVICE counter, overwritten with the
+ * number of records the problem emits (it may exceed capacity: the surplus is dropped — size with a NULL pass).
+ */
+int d2d_paths(const D2DProblem *p, float min_valid, int32_t emit_all, D2DPathRecord *records, int64_t capacity,
+              unsigned long long *count, void *stream);
+
+/*
  * Host-buffer convenience entry used for end-to-end timing and by callers without device arrays:
  * every pointer of `p` and every output is a HOST pointer; the call stages inputs to the device,
  * runs forward (and backward when any *_bar / want_grad output is non-NULL), copies results back

@@ -585,6 +585,98 @@ def test_activity_mask_backward_equals_full_retrace(mode, case):
             assert torch.equal(both["Z"], full["Z"]) and torch.equal(both["grid"], full["grid"])
 
 
+# ---- path materialisation (Scene.all_paths / all_valid_paths, generic fun) ---------------------------------------
+@pytest.mark.parametrize("min_order,max_order", [(0, 0), (1, 1), (2, 2), (0, 2)])
+def test_all_paths_and_valid_paths_kat(min_order, max_order):
+    """tests/test_scene.py:401-441 of the reference: every yielded path has the right order, its validity equals
+    is_valid of the same path (here: the oracle's, bit for bit, hard logic), and all_valid_paths yields exactly
+    the valid ones in the same order."""
+    sc = d.Scene.square_scene()
+    osc = H.oracle_scene_from_product(sc)
+    valid_paths = sc.all_valid_paths(approx=False, min_order=min_order, max_order=max_order, key=1234)
+    n = 0
+    for tx_key, rx_key, got_valid, path, cand in sc.all_paths(min_order=min_order, max_order=max_order, approx=False):
+        n += 1
+        assert tx_key == "tx" and rx_key == "rx"
+        assert min_order <= path.xys.shape[0] - 2 <= max_order and min_order <= len(cand) <= max_order
+        xo, lo = R.from_tx_objects_rx(osc, "image", osc.transmitters["tx"], cand, osc.receivers["rx"])
+        xo = torch.stack([p.reshape(2) for p in xo]).numpy()
+        assert np.array_equal(path.xys, xo), (cand, path.xys, xo)
+        assert np.float32(path.loss) == np.float32(lo)
+        want = bool(R.is_valid(osc, cand, [torch.from_numpy(r) for r in xo], lo, R.Logic(False)))
+        assert got_valid is want or got_valid == want
+        if got_valid:
+            _, _, got_path, got_cand = next(valid_paths)
+            assert np.array_equal(got_path.xys, path.xys) and np.array_equal(got_cand, cand)
+    assert n == sum(1 if k == 0 else 4 * 3 ** (k - 1) for k in range(min_order, max_order + 1))
+    with pytest.raises(StopIteration):
+        next(valid_paths)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_paths_records_reproduce_the_forward_map(mode):
+    """Size-independent property: summing valid * value of the emitted records per (fixed, grid point), in
+    candidate order, gives the forward map bit for bit (the records hold exactly what the fused kernel adds);
+    emit_all returns T x R x C records whose validities equal valid_out."""
+    sc = SCENES["basic"]
+    sc = d.Scene({"a": d.Point(xy=[0.1, 0.1]), "b": d.Point(xy=[0.65, 0.35])}, sc.receivers, sc.objects)
+    X, Y = H.jittered_grid(sc, 20, 24, seed=4)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    cfg = _cfg(mode, max_order=2, grid_cols=24)
+    Z, v = F.power_fwd(cfg, xys, fixed, grid, alpha=30.0, want_valid=True, device="cuda")
+    rec = F.paths(cfg, xys, fixed, grid, alpha=30.0, min_valid=0.0, device="cuda")
+    T, Rn, C = v.shape
+    assert rec["num_candidates"] == C and int((v != 0).sum()) == rec["valid"].numel()
+    Zr = np.zeros((T, Rn), np.float32)
+    f, g, val, w = (rec[k].cpu().numpy() for k in ("fixed", "grid", "valid", "value"))
+    for i in range(len(f)):  # records are sorted by (fixed, grid, candidate): the kernel's accumulation order
+        Zr[f[i], g[i]] = np.float32(Zr[f[i], g[i]] + np.float32(val[i] * w[i]))
+    assert np.array_equal(Zr, Z.cpu().numpy())
+    assert torch.equal(rec["valid"], v[rec["fixed"].long(), rec["grid"], rec["candidate"]])
+    sub = grid[:50]
+    ra = F.paths(cfg, xys, fixed, sub, alpha=30.0, emit_all=True, device="cuda")
+    _, va = F.power_fwd(_cfg(mode, max_order=2), xys, fixed, sub, alpha=30.0, want_valid=True, device="cuda")
+    assert ra["valid"].numel() == T * 50 * C
+    assert torch.equal(ra["valid"].reshape(T, 50, C), va)
+    k = ra["order"].long()
+    lens = ra["length"]
+    d2 = (ra["xys"][:, 1:] - ra["xys"][:, :-1]) + 1.1920929e-07
+    seg = d2.square().sum(-1).sqrt()
+    m = (torch.arange(5, device=seg.device)[None, :] <= k[:, None]).float()
+    assert torch.allclose((seg * m).sum(-1), lens, rtol=1e-6)
+
+
+def test_generic_fun_escape_hatch():
+    """an arbitrary `fun` evaluated on PathBatch tensors gives the fused kernel's map when it restates
+    utils.received_power (rtol 1e-6: summation order of index_add_), and the reference's LOS KAT for length**2."""
+    sc = SCENES["obstacle"]
+    X, Y = _grid(sc, 30, 28, "jitter")
+
+    def my_power(paths, r_coef=0.5, height=0.1):
+        r = paths.length()
+        return (r_coef ** paths.order) / (height * height + r * r)
+
+    for approx in (False, True):
+        got = sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=my_power, reduce_all=True, max_order=2, approx=approx)
+        want = sc.accumulate_on_receivers_grid_over_paths(X, Y, reduce_all=True, max_order=2, approx=approx)
+        np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+    res = list(d.Scene.square_scene().accumulate_on_receivers_grid_over_paths(
+        X, Y, fun=lambda p, s: s * p.length() ** 2, fun_args=(2.0,), max_order=0, approx=False))
+    assert [k for k, _ in res] == ["tx"]
+    np.testing.assert_allclose(res[0][1], 2.0 * ((X - 0.2) ** 2 + (Y - 0.2) ** 2), rtol=1e-5, atol=1e-6)
+    with pytest.raises(NotImplementedError):
+        sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=my_power, grad=True)
+
+
+def test_all_valid_paths_fermat_on_vertex_scene():
+    sc = _vertex_scene()
+    got = list(sc.all_valid_paths(approx=False, path_cls=d.FermatPath, max_order=1, key=1234))
+    assert len(got) >= 1 and all(isinstance(p, d.FermatPath) for _, _, p, _ in got)
+    assert all(p.xys.shape == (len(c) + 2, 2) for _, _, p, c in got)
+
+
 def test_scene_api_solver_methods():
     sc = _vertex_scene()
     X, Y = sc.grid(24, 20)

@@ -73,8 +73,11 @@ def test_mode_resolution():
 def test_unsupported_requests_raise():
     sc = d.Scene.square_scene()
     X, Y = sc.grid(4)
+    # an arbitrary callable selects the generic escape hatch (paths materialised on the GPU, fun on PathBatch)
+    sc._config("receivers", lambda *a: 0.0, (), None, False, d.ImagePath, None, 0, 1, None, None, {})
+    assert sc._generic
     with pytest.raises(NotImplementedError):
-        sc._config("receivers", lambda *a: 0.0, (), None, False, d.ImagePath, None, 0, 1, None, None, {})
+        sc._config("receivers", "not a function", (), None, False, d.ImagePath, None, 0, 1, None, None, {})
     with pytest.raises(NotImplementedError):
         sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"many": 3}, 0, 1, None, None, {})
     with pytest.raises(TypeError):
