@@ -61,6 +61,7 @@ class D2DProblem(C.Structure):
         ("no_cull", C.c_int32),
         ("candidate_slices", C.c_int32),
         ("active_mask", C.c_void_p),
+        ("many", C.c_int32),
     ]
 
 

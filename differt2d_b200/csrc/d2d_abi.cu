@@ -143,6 +143,7 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
     k.min_order = p->min_order;
     k.max_order = p->max_order;
     k.steps = p->steps;
+    k.many = p->many > 1 ? p->many : 1;
     k.fun = p->fun;
     k.reduce_all = p->reduce_all ? 1 : 0;
     k.alpha = p->alpha;
@@ -374,7 +375,7 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
     // input arena
     const size_t o_xys = 0, o_kind = o_xys + al(N * 16), o_phi = o_kind + al(N), o_fix = o_phi + al(N * 4),
                  o_grid = o_fix + al(T * 8), o_x0 = o_grid + al(R * 8),
-                 o_zbar = o_x0 + al(hp->x0 ? (size_t)C * hp->max_order * 4 : 0),
+                 o_zbar = o_x0 + al(hp->x0 ? (size_t)C * (hp->many > 1 ? hp->many : 1) * hp->max_order * 4 : 0),
                  in_total = o_zbar + al(Zbar ? Tout * R * 4 : 0);
     int rc = g_in.ensure(in_total, device);
     if (rc) return cuda_fail(rc, "cudaMalloc(inputs)");
@@ -387,7 +388,7 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
     h2d(o_phi, hp->object_phis, N * 4);
     h2d(o_fix, hp->fixed_xy, T * 8);
     h2d(o_grid, hp->grid_xy, R * 8);
-    if (hp->x0) h2d(o_x0, hp->x0, (size_t)C * hp->max_order * 4);
+    if (hp->x0) h2d(o_x0, hp->x0, (size_t)C * (hp->many > 1 ? hp->many : 1) * hp->max_order * 4);
     if (Zbar) h2d(o_zbar, Zbar, Tout * R * 4);
     dp.objects_xys = (const float*)(din + o_xys);
     dp.object_kinds = hp->object_kinds ? (const uint8_t*)(din + o_kind) : nullptr;

@@ -46,7 +46,8 @@ __device__ __noinline__ float path_vjp(const SceneTab& T, const KParams& p, cons
     float solver_loss = 0.f;
     const int stride = adam_ckpt_stride(p.steps);
     if constexpr (kSolver) {
-        solver_loss = adam_scan_ckpt<METHOD, K>(T, p, cd, tx, rx, col, stride, ck, th_final);
+        const int restart = p.many > 1 ? best_restart<METHOD, K>(T, p, cd, tx, rx, col) : 0;
+        solver_loss = adam_scan_ckpt<METHOD, K>(T, p, cd, tx, rx, col, restart, stride, ck, th_final);
         place_points<K>(T, cd, th_final.th, X);
     } else {
 #pragma unroll

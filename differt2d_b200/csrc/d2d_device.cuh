@@ -52,6 +52,7 @@ struct KParams {
     int N, T;
     int min_order, max_order;
     int steps;
+    int many;              // restarts of the Fermat/MinPath scan (>= 1)
     int fun, reduce_all;
     long long C_total;     // candidates over all orders (columns of valid_out)
     float alpha, tol, patch, lr;

@@ -69,7 +69,13 @@ __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams&
     }
     constexpr int KK = K > 0 ? K : 1;
     float th[KK], mu[KK], nu[KK];
-    {
+    float best_th[KK];
+    float best = 0.0f, last = 0.0f;
+    X[0] = tx;
+    X[K + 1] = rx;
+    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;  // optax.adam defaults
+    // minimize_many_random_uniform (optimize.py:142-182): `many` independent scans, keep argmin of the final losses
+    for (int r = 0; r < p.many; ++r) {
         int u = 0;
 #pragma unroll
         for (int i = 0; i < K; ++i) {
@@ -77,33 +83,41 @@ __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams&
             nu[i] = 0.f;
             th[i] = 0.f;
             if (T.kind[cd.c[i]] != D2D_KIND_VERTEX) {
-                th[i] = p.x0 ? p.x0[col * p.max_order + u] : 0.5f;
+                th[i] = p.x0 ? p.x0[(col * p.many + r) * p.max_order + u] : 0.5f;
                 ++u;
             }
         }
-    }
-    X[0] = tx;
-    X[K + 1] = rx;
-    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;  // optax.adam defaults
-    float b1p = 1.0f, b2p = 1.0f;
-    float last = 0.0f;
-    for (int s = 0; s < p.steps; ++s) {
-        place_points<K>(T, cd, th, X);
-        float2 G[K + 2];
-        last = solver_loss_grad<METHOD, K>(T, cd, X, G);
-        b1p *= b1;
-        b2p *= b2;
-        const float bc1 = 1.0f - b1p, bc2 = 1.0f - b2p;
+        float b1p = 1.0f, b2p = 1.0f;
+        for (int s = 0; s < p.steps; ++s) {
+            place_points<K>(T, cd, th, X);
+            float2 G[K + 2];
+            last = solver_loss_grad<METHOD, K>(T, cd, X, G);
+            b1p *= b1;
+            b2p *= b2;
+            const float bc1 = 1.0f - b1p, bc2 = 1.0f - b2p;
 #pragma unroll
-        for (int i = 0; i < K; ++i) {
-            if (T.kind[cd.c[i]] == D2D_KIND_VERTEX) continue;
-            const float4 w0 = T.w0[cd.c[i]];
-            const float g = G[i + 1].x * w0.z + G[i + 1].y * w0.w;
-            mu[i] = (1.0f - b1) * g + b1 * mu[i];
-            nu[i] = (1.0f - b2) * (g * g) + b2 * nu[i];
-            const float mh = mu[i] / bc1, nh = nu[i] / bc2;
-            th[i] = th[i] + (-p.lr) * (mh / (sqrtf(nh) + eps));
+            for (int i = 0; i < K; ++i) {
+                if (T.kind[cd.c[i]] == D2D_KIND_VERTEX) continue;
+                const float4 w0 = T.w0[cd.c[i]];
+                const float g = G[i + 1].x * w0.z + G[i + 1].y * w0.w;
+                mu[i] = (1.0f - b1) * g + b1 * mu[i];
+                nu[i] = (1.0f - b2) * (g * g) + b2 * nu[i];
+                const float mh = mu[i] / bc1, nh = nu[i] / bc2;
+                th[i] = th[i] + (-p.lr) * (mh / (sqrtf(nh) + eps));
+            }
         }
+        if (p.many == 1) break;
+        // jnp.argmin: first minimum; a NaN loss wins (NaN propagates through argmin)
+        if (r == 0 || (last < best && best == best) || (last != last && best == best)) {
+            best = last;
+#pragma unroll
+            for (int i = 0; i < K; ++i) best_th[i] = th[i];
+        }
+    }
+    if (p.many > 1) {
+        last = best;
+#pragma unroll
+        for (int i = 0; i < K; ++i) th[i] = best_th[i];
     }
     place_points<K>(T, cd, th, X);
     if (METHOD == D2D_METHOD_FERMAT) {

@@ -232,7 +232,7 @@ __device__ __forceinline__ float adam_step(const SceneTab& T, const KParams& p, 
 
 template <int K>
 __device__ __forceinline__ void adam_init(const SceneTab& T, const KParams& p, const Cand<K>& cd, const long long col,
-                                          AdamState<K>& st) {
+                                          const int restart, AdamState<K>& st) {
     int u = 0;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
@@ -240,7 +240,7 @@ __device__ __forceinline__ void adam_init(const SceneTab& T, const KParams& p, c
         st.nu[i] = 0.f;
         st.th[i] = 0.f;
         if (T.kind[cd.c[i]] != D2D_KIND_VERTEX) {
-            st.th[i] = p.x0 ? p.x0[col * p.max_order + u] : 0.5f;
+            st.th[i] = p.x0 ? p.x0[(col * p.many + restart) * p.max_order + u] : 0.5f;
             ++u;
         }
     }
@@ -251,9 +251,9 @@ __device__ __forceinline__ void adam_init(const SceneTab& T, const KParams& p, c
 // Forward scan that keeps checkpoints.  ck[c] = state before step c * stride.  Returns losses[-1].
 template <int METHOD, int K>
 __device__ __forceinline__ float adam_scan_ckpt(const SceneTab& T, const KParams& p, const Cand<K>& cd, const float2 tx,
-                                                const float2 rx, const long long col, const int stride,
-                                                AdamState<K> (&ck)[kNck], AdamState<K>& st) {
-    adam_init<K>(T, p, cd, col, st);
+                                                const float2 rx, const long long col, const int restart,
+                                                const int stride, AdamState<K> (&ck)[kNck], AdamState<K>& st) {
+    adam_init<K>(T, p, cd, col, restart, st);
     float last = 0.f;
     int c = 0, next = 0;
     for (int s = 0; s < p.steps; ++s) {
@@ -264,6 +264,27 @@ __device__ __forceinline__ float adam_scan_ckpt(const SceneTab& T, const KParams
         last = adam_step<METHOD, K>(T, p, cd, tx, rx, st);
     }
     return last;
+}
+
+// minimize_many_random_uniform (optimize.py:171-182): index of the restart whose final loss is the smallest
+// (first one on ties, NaN wins: jnp.argmin).  argmin is piecewise constant, so the cotangent flows through the
+// selected scan only; the selection itself is re-derived here by plain scans (nothing is stored by the forward).
+template <int METHOD, int K>
+__device__ __forceinline__ int best_restart(const SceneTab& T, const KParams& p, const Cand<K>& cd, const float2 tx,
+                                            const float2 rx, const long long col) {
+    int arg = 0;
+    float best = 0.0f;
+    for (int r = 0; r < p.many; ++r) {
+        AdamState<K> st;
+        adam_init<K>(T, p, cd, col, r, st);
+        float last = 0.0f;
+        for (int s = 0; s < p.steps; ++s) last = adam_step<METHOD, K>(T, p, cd, tx, rx, st);
+        if (r == 0 || (last < best && best == best) || (last != last && best == best)) {
+            best = last;
+            arg = r;
+        }
+    }
+    return arg;
 }
 
 __host__ __device__ inline int adam_ckpt_stride(int steps) {

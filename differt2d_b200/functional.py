@@ -32,6 +32,7 @@ class TraceConfig:
     filter_nodes: tuple = ()
     method: str = "image"
     steps: int = 100
+    many: int = 1  # Fermat/MinPath restarts (optimize.py:142-182); x0 is then [C, many, max_order]
     lr: float = 0.1
     mode: str = "hard"
     tol: float = 1e-2
@@ -96,6 +97,7 @@ class _Packed:
         p.n_filter = int(self.filter.size)
         p.method = METHODS[cfg.method]
         p.steps = int(cfg.steps)
+        p.many = int(cfg.many)
         p.lr = float(cfg.lr)
         p.x0 = self.x0.data_ptr() if self.x0 is not None else None
         p.mode = MODES[cfg.mode]

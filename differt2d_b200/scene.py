@@ -218,9 +218,9 @@ class Scene:
             raise NotImplementedError("path_cls must be ImagePath, FermatPath or MinPath")
         pk = dict(path_cls_kwargs or {})
         steps = int(pk.pop("steps", 100))
-        many = int(pk.pop("many", 1))
-        if many != 1:
-            raise NotImplementedError("many > 1 restarts (optimize.py:171-182) are listed under DESIGN.md 'next'")
+        many = int(pk.pop("many", 1))  # geometry.py:1198 / :1282: the path classes default to a single run
+        if many < 1:
+            raise ValueError("many must be >= 1")
         optimizer = pk.pop("optimizer", None)
         if optimizer is not None or pk:
             raise NotImplementedError(f"unsupported path_cls_kwargs: {sorted(pk) + (['optimizer'] if optimizer else [])}")
@@ -235,8 +235,8 @@ class Scene:
                                      if i not in self._filter_nodes(filter_objects)):
             raise TypeError("ImagePath cannot interact with Vertex objects (geometry.py:1020 expects walls)")
         cfg = F.TraceConfig(grid_role=grid_role, min_order=min_order, max_order=max_order,
-                            filter_nodes=self._filter_nodes(filter_objects), method=method, steps=steps, lr=0.1,
-                            mode=mode, tol=tol, patch=patch, fun="received_power" if fname == "generic" else fname,
+                            filter_nodes=self._filter_nodes(filter_objects), method=method, steps=steps, many=many,
+                            lr=0.1, mode=mode, tol=tol, patch=patch, fun="received_power" if fname == "generic" else fname,
                             r_coef=r_coef, height=height, reduce_all=bool(reduce_all))
         self._generic = fname == "generic"
         return cfg, alpha
@@ -260,7 +260,8 @@ class Scene:
         return Z.sum(0) if cfg.reduce_all else Z
 
     def _x0(self, cfg: F.TraceConfig, key, device):
-        """Initial guesses per candidate (optimize.py:132); `key` is an int seed or an explicit [C,max_order] table."""
+        """Initial guesses per candidate and restart (optimize.py:132, :173-177); `key` is an int seed or an explicit
+        [C, max_order] (many == 1) / [C, many, max_order] table."""
         if cfg.method == "image" or cfg.max_order == 0:
             return None
         n_allowed = len(self.objects) - len(cfg.filter_nodes)
@@ -269,11 +270,12 @@ class Scene:
         del n_allowed
         if key is None:
             raise TypeError("FermatPath / MinPath need `key` (an int seed or an explicit x0 table)")
+        shape = (C, cfg.max_order) if cfg.many == 1 else (C, cfg.many, cfg.max_order)
         if isinstance(key, (int, np.integer)):
-            return np.random.default_rng(int(key)).random((C, cfg.max_order), dtype=np.float32)
+            return np.random.default_rng(int(key)).random(shape, dtype=np.float32)
         x0 = np.asarray(key.detach().cpu() if hasattr(key, "detach") else key, dtype=np.float32)
-        if x0.shape != (C, cfg.max_order):
-            raise ValueError(f"x0 table must have shape {(C, cfg.max_order)}, got {x0.shape}")
+        if x0.shape != shape:
+            raise ValueError(f"x0 table must have shape {shape}, got {x0.shape}")
         return x0
 
     def _grid_call(self, grid_role, X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad, path_cls,

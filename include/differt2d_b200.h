@@ -85,7 +85,7 @@ typedef struct D2DProblem {
     int32_t method;  /* D2D_METHOD_*                                                              */
     int32_t steps;   /* Adam iterations, optimize.py:49 (default 100)                             */
     float lr;        /* Adam learning rate, optimize.py:83 (0.1)                                  */
-    const float *x0; /* [C,max_order] initial guesses per candidate (optimize.py:132), Fermat/Min */
+    const float *x0; /* [C,many,max_order] initial guesses per candidate and restart (optimize.py:132, :173-177) */
     /* ---- validity logic: Path.is_valid (geometry.py:908-963) --------------------------------- */
     int32_t mode;           /* D2D_MODE_*                                                         */
     float alpha;            /* activation slope (defaults.py:3); must be > 0                      */
@@ -108,6 +108,9 @@ typedef struct D2DProblem {
                            /* forward over the SAME inputs filled, re-traces only the set bits instead of the whole     */
                            /* candidate list (identical results; the reference keeps a full tape of every intermediate */
                            /* at [n,m] size instead, scene.py:1920-1952).  NULL: the backward re-traces everything.     */
+    int32_t many; /* Fermat/MinPath restarts, optimize.py:142-182 (minimize_many_random_uniform): the scan runs    */
+                  /* `many` times from x0[c, 0..many-1] and the iterate with the smallest final loss is kept       */
+                  /* (first one on ties, jnp.argmin).  0 or 1 = a single run (the path classes' default, :1198).   */
 } D2DProblem;
 
 /* Fills a problem with the reference's defaults (defaults.py, geometry.py:915, optimize.py:49,83). */

@@ -536,7 +536,29 @@ def fermat_or_min_path(scene: OScene, method, tx, cand, rx, x0, steps=100, lr=0.
         return out.expand(shape) if out.dim() == 0 else out
 
     loss_fun = fermat_loss if method == "fermat" else min_loss
-    theta0 = _t(x0)[:n_unknowns].expand(*shape, n_unknowns).clone()
+    x0t = _t(x0)
+    if x0t.dim() == 2:
+        # minimize_many_random_uniform (optimize.py:142-182): x0 [many, n]; vmap over the restarts, then
+        # i_min = argmin(losses) (first minimum), xs[i_min], losses[i_min] — per grid element
+        thetas, losses = [], []
+        for r in range(x0t.shape[0]):
+            th0 = x0t[r, :n_unknowns].expand(*shape, n_unknowns).clone()
+            if n_unknowns == 0:
+                th, ls = th0, loss_fun(th0)
+            else:
+                th, ls = minimize_adam(loss_fun, th0, steps=steps, lr=lr, differentiable=differentiable)
+            thetas.append(th)
+            losses.append(ls.expand(shape) if ls.dim() == 0 else ls)
+        L = torch.stack(losses)                       # [many, ...]
+        i_min = torch.argmin(L.detach(), dim=0, keepdim=True)
+        loss = torch.gather(L, 0, i_min).squeeze(0)
+        TH = torch.stack(thetas)                      # [many, ..., n]
+        theta = torch.gather(TH, 0, i_min.unsqueeze(-1).expand(1, *shape, n_unknowns)).squeeze(0)
+        xys = parametric_to_cartesian(scene, cand, theta, tx, rx)
+        if method == "fermat":
+            return xys, path_loss(scene, cand, xys)
+        return xys, loss
+    theta0 = x0t[:n_unknowns].expand(*shape, n_unknowns).clone()
     if n_unknowns == 0:
         # scan still runs, on an empty parameter vector; loss is the constant function value
         theta = theta0

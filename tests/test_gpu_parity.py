@@ -511,6 +511,41 @@ def test_solver_vjp_order3():
             assert e < 2e-3, (method, k, e, err)
 
 
+@pytest.mark.parametrize("method", ["fermat", "minpath"])
+def test_solver_many_restarts(method):
+    """optimize.minimize_many_random_uniform (optimize.py:142-182): `many` scans per candidate, argmin of the final
+    losses.  Short scans (the iterate noise of long ones would flip the argmin between implementations): forward
+    flags/maps and the VJP through the SELECTED scan vs the oracle; and many = 3 with three equal guesses must
+    reproduce many = 1 bit for bit."""
+    sc = H.generic_position(_vertex_scene())
+    osc = H.oracle_scene_from_product(sc)
+    X, Y = H.jittered_grid(sc, 6, 8, seed=3)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    C, many = 50, 3
+    x0 = np.random.default_rng(99).random((C, many, 2), dtype=np.float32)
+    cfg = _cfg("hard_sigmoid", max_order=2, method=method, steps=8, many=many, grid_cols=8, reduce_all=True)
+    Zbar = (0.5 + np.random.default_rng(7).random(X.shape)).astype(np.float32)
+    got = F.power_bwd(cfg, xys, fixed, grid, Zbar.reshape(-1), kinds=kinds, phis=phis, x0=x0, alpha=50.0, device="cuda")
+    Zo, go = R.power_map_and_vjp(osc, X, Y, Zbar, method=method, max_order=2, x0=x0, steps=8, approx=True, alpha=50.0)
+    Zf = F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, x0=x0, alpha=50.0, device="cuda")
+    assert torch.equal(Zf, got["Z"])
+    np.testing.assert_allclose(got["Z"].cpu().numpy(), Zo.numpy().reshape(-1), rtol=1e-4, atol=1e-5)
+    for k, w in (("grid", go["grid"]), ("objects", go["xys"]), ("fixed", go["fixed"]), ("alpha", go["alpha"])):
+        a, b = got[k].cpu().numpy().reshape(-1), w.numpy().reshape(-1)
+        # (largest-entry relative; measured 1e-5..1e-3: 8-step iterates sit on steep activation slopes)
+        assert np.abs(a - b).max() <= 5e-3 * max(np.abs(b).max(), 1e-30), k
+    # the restarts really matter: a single run from the first guess gives a different map
+    one = F.power_fwd(_cfg("hard_sigmoid", max_order=2, method=method, steps=8, grid_cols=8, reduce_all=True), xys,
+                      fixed, grid, kinds=kinds, phis=phis, x0=np.ascontiguousarray(x0[:, 0]), alpha=50.0, device="cuda")
+    assert not torch.equal(one, Zf)
+    same = np.repeat(x0[:, :1], many, axis=1)
+    rep = F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, x0=same, alpha=50.0, device="cuda")
+    assert torch.equal(rep, one)
+
+
 def test_solver_autograd_function():
     """power_map (the custom_vjp analogue) differentiates FermatPath maps end to end."""
     sc = H.generic_position(_vertex_scene())

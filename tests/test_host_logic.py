@@ -78,8 +78,10 @@ def test_unsupported_requests_raise():
     assert sc._generic
     with pytest.raises(NotImplementedError):
         sc._config("receivers", "not a function", (), None, False, d.ImagePath, None, 0, 1, None, None, {})
+    cfg3, _ = sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"many": 3}, 0, 1, None, None, {})
+    assert cfg3.many == 3 and sc._x0(cfg3, 7, None).shape == (5, 3, 1)  # optimize.py:142-182 restarts
     with pytest.raises(NotImplementedError):
-        sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"many": 3}, 0, 1, None, None, {})
+        sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"optimizer": object()}, 0, 1, None, None, {})
     with pytest.raises(TypeError):
         sc._config("receivers", d.received_power, (), None, False, d.ImagePath, None, 0, 1, None, None, {"bogus": 1})
     with pytest.raises(TypeError):
