@@ -66,53 +66,85 @@ def flops_per_receiver(n: int, max_order: int, smooth: bool) -> float:
 
 
 class ClockSampler:
-    FIELDS = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
-              "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
-              "clocks_event_reasons.sw_power_cap")
+    """
+    SM clock / throttle-reason samples taken DURING the timed region.  The region lasts tens of milliseconds, far
+    below what `nvidia-smi -lms` can resolve, so NVML is polled in-process (nvidia_ml_py) from a thread, about
+    every millisecond, between mark_start() and mark_stop(); `nvidia-smi` is the fallback when NVML cannot load.
+    """
 
-    def __init__(self, index: int):
-        self.index = index
-        self.rows = []
-        self.proc = None
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
+
+    def __init__(self, index: int, uuid: str | None = None):
+        self.index, self.uuid = index, uuid
+        self.sm, self.bits, self.power = [], 0, []
+        self.sm_max = None
+        self.live = False
+        self.done = False
+        self.thread = None
+        self.source = None
+        self.h = None
 
     def start(self):
         try:
-            self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.FIELDS}", "--format=csv,noheader,nounits",
-                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.thread = threading.Thread(target=self._read, daemon=True)
+            import pynvml as N
+
+            N.nvmlInit()
+            h = None
+            if self.uuid:
+                try:
+                    h = N.nvmlDeviceGetHandleByUUID(self.uuid if self.uuid.startswith("GPU-") else "GPU-" + self.uuid)
+                except Exception:
+                    h = None
+            self.h = h if h is not None else N.nvmlDeviceGetHandleByIndex(self.index)
+            self.N = N
+            self.sm_max = float(N.nvmlDeviceGetMaxClockInfo(self.h, N.NVML_CLOCK_SM))
+            self.source = "nvml"
+            self.thread = threading.Thread(target=self._poll, daemon=True)
             self.thread.start()
         except Exception:
-            self.proc = None
+            self.h = None
+            self.source = "nvidia-smi"
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append(line.strip())
+    def _poll(self):
+        N = self.N
+        while not self.done:
+            if self.live:
+                try:
+                    self.sm.append(float(N.nvmlDeviceGetClockInfo(self.h, N.NVML_CLOCK_SM)))
+                    self.bits |= int(N.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                    self.power.append(N.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+                except Exception:
+                    pass
+            time.sleep(0.0005)
+
+    def mark_start(self):
+        self.live = True
+
+    def mark_stop(self):
+        self.live = False
+
+    def _smi_once(self) -> dict:
+        try:
+            out = subprocess.run(
+                ["nvidia-smi", f"--id={self.index}", "--query-gpu=clocks.sm,clocks.max.sm", "--format=csv,noheader,nounits"],
+                capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+            return {"sm_mhz": float(out[0]), "sm_max_mhz": float(out[1]), "reasons": [], "samples": 1,
+                    "source": "nvidia-smi single query right after the timed region (NVML unavailable)"}
+        except Exception:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvml and nvidia-smi unavailable"], "samples": 0}
 
     def stop(self) -> dict:
-        if self.proc is None:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=2)
-        except Exception:
-            self.proc.kill()
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            parts = [p.strip() for p in r.split(",")]
-            if len(parts) < 7:
-                continue
-            try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
-            except ValueError:
-                continue
-            for nm, v in zip(names, parts[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(nm)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+        self.done = True
+        if self.h is None:
+            return self._smi_once()
+        if self.thread is not None:
+            self.thread.join(timeout=1)
+        reasons = sorted(nm for nm, bit in self.REASONS if self.bits & bit)
+        return {"sm_mhz": float(np.median(self.sm)) if self.sm else None, "sm_max_mhz": self.sm_max,
+                "reasons": reasons, "samples": len(self.sm),
+                "power_w_max": max(self.power) if self.power else None,
+                "source": "NVML polled in-process during the timed region"}
 
 
 def bench_reference(args, rank: int, world: int) -> None:
@@ -167,7 +199,7 @@ def workload_config(args, world):
                     f"(785 candidates), {MODE} alpha={ALPHA:g}, forward + VJP, "
                     f"{GRID_PER_GPU[0]}x{GRID_PER_GPU[1]} receivers per GPU",
         "grid_global": [GRID_PER_GPU[0] * world, GRID_PER_GPU[1]],
-        "sharding": f"receiver-grid rows over {world} GPU(s); NCCL all-reduce of scene-parameter cotangents",
+        "sharding": f"receiver-grid rows over {world} GPU(s), bands of 8 rows dealt round robin; NCCL all-reduce of scene-parameter cotangents",
         "l2": f"L2 flushed between timed steps ({FLUSH_BYTES >> 20} MiB memset, inside the timed region)",
     }
 
@@ -215,7 +247,7 @@ def cpu_baseline_sample(sc, args) -> dict:
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--coords", default="raw", choices=["raw", "normalised"])
@@ -246,8 +278,8 @@ def main() -> None:
     fixed = np.stack([p.xy for p in sc.transmitters.values()])
     n_rows, n_cols = GRID_PER_GPU[0] * world, GRID_PER_GPU[1]
     X, Y = sc.grid(n_cols, n_rows)
-    r0, r1 = D.row_block(n_rows, world, rank)
-    grid_h = np.stack([X[r0:r1], Y[r0:r1]], -1).reshape(-1, 2).astype(np.float32)
+    rows = D.row_tiles_cyclic(n_rows, world, rank)  # bands of 8 rows, round robin: equal work on every rank
+    grid_h = np.stack([X[rows], Y[rows]], -1).reshape(-1, 2).astype(np.float32)
     R = grid_h.shape[0]
     cfg = F.TraceConfig(mode=MODE, max_order=MAX_ORDER, reduce_all=True, grid_cols=n_cols)
     n_obj = xys.shape[0]
@@ -308,9 +340,14 @@ def main() -> None:
     torch.cuda.synchronize(dev)
     if dist is not None:
         D.barrier()
-    sampler = ClockSampler(local)
+    try:
+        uuid = str(torch.cuda.get_device_properties(dev).uuid)
+    except Exception:
+        uuid = None
+    sampler = ClockSampler(local, uuid)
     if rank == 0:
         sampler.start()
+        sampler.mark_start()
     launches0 = F.launch_count()
     t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize(dev)
@@ -321,6 +358,7 @@ def main() -> None:
     torch.cuda.synchronize(dev)
     if dist is not None:
         D.barrier()
+    sampler.mark_stop()
     launches = F.launch_count() - launches0
     clocks = sampler.stop() if rank == 0 else None
     elapsed_ms = t_start.elapsed_time(t_end)

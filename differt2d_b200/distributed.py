@@ -1,6 +1,6 @@
 """
-Multi-GPU plumbing: one process per GPU, the receiver grid sharded by contiguous row blocks
-(SURVEY §8e).  Forward maps and per-receiver cotangents need no communication (disjoint rows);
+Multi-GPU plumbing: one process per GPU, the receiver grid sharded by rows: bands of 8 rows
+dealt round robin for load balance (row_tiles_cyclic), or contiguous blocks (row_block).  Forward maps and per-receiver cotangents need no communication (disjoint rows);
 the scene-parameter cotangents (object vertices, RIS angles, fixed points, alpha — a few KB) are
 partial sums and take ONE all-reduce per backward call (NCCL over NVLink on GPUs, gloo in CPU tests).
 """
@@ -10,6 +10,7 @@ from __future__ import annotations
 import os
 from typing import Optional, Tuple
 
+import numpy as np
 import torch
 import torch.distributed as dist
 
@@ -19,6 +20,17 @@ def row_block(n_rows: int, world: int, rank: int) -> Tuple[int, int]:
     base, extra = divmod(n_rows, world)
     r0 = rank * base + min(rank, extra)
     return r0, r0 + base + (1 if rank < extra else 0)
+
+
+def row_tiles_cyclic(n_rows: int, world: int, rank: int, tile_rows: int = 8) -> "np.ndarray":
+    """
+    Row indices of `rank` when the grid is dealt out in bands of `tile_rows` rows, round robin (band b goes to
+    rank b % world).  The kernels' 16 x 8 tiles stay whole, and every rank sees a statistically identical slice of
+    the scene: the culls remove a very different share of the work in different places, so contiguous blocks
+    (row_block) leave the ranks unevenly loaded while the step time is the maximum over ranks.
+    """
+    rows = np.arange(n_rows)
+    return rows[(rows // tile_rows) % world == rank]
 
 
 def init(world: Optional[int] = None, rank: Optional[int] = None, backend: Optional[str] = None):
@@ -74,24 +86,31 @@ def shutdown() -> None:
         dist.destroy_process_group()
 
 
-def sharded_power_vjp(cfg, xys, fixed, X, Y, Zbar=None, *, alpha=100.0, kinds=None, phis=None, device=None):
+def sharded_power_vjp(cfg, xys, fixed, X, Y, Zbar=None, *, alpha=100.0, kinds=None, phis=None, device=None,
+                      layout: str = "cyclic"):
     """
-    Row-sharded forward + VJP: this rank traces rows row_block(n, world, rank) of the (n, m) grid and
-    returns its slice of Z / grid_bar plus the ALL-REDUCED scene-parameter cotangents.
+    Row-sharded forward + VJP: this rank traces its rows of the (n, m) grid (`layout="cyclic"`: bands of 8 rows
+    dealt round robin, row_tiles_cyclic; `"block"`: one contiguous block, row_block) and returns its slice of
+    Z / grid_bar plus the ALL-REDUCED scene-parameter cotangents; out["rows"] holds the row indices it owns.
     """
     from . import functional as F
 
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
     n = X.shape[0]
-    r0, r1 = row_block(n, world, rank)
-    Xs, Ys = torch.as_tensor(X[r0:r1]), torch.as_tensor(Y[r0:r1])
+    if layout == "cyclic":
+        rows = row_tiles_cyclic(n, world, rank)
+    elif layout == "block":
+        rows = np.arange(*row_block(n, world, rank))
+    else:
+        raise ValueError("layout must be 'cyclic' or 'block'")
+    Xs, Ys = torch.as_tensor(np.asarray(X)[rows]), torch.as_tensor(np.asarray(Y)[rows])
     grid = torch.stack((Xs, Ys), dim=-1).reshape(-1, 2)
-    zb = None if Zbar is None else torch.as_tensor(Zbar[r0:r1]).reshape(-1)
+    zb = None if Zbar is None else torch.as_tensor(np.asarray(Zbar)[rows]).reshape(-1)
     out = F.power_bwd(cfg, xys, fixed, grid, zb, kinds=kinds, phis=phis, alpha=alpha, device=device)
     n_obj = out["objects"].shape[0]
     buf = pack_param_grads(out["objects"], out["phis"], out["fixed"], out["alpha"])
     allreduce_sum_(buf)
     out["objects"], out["phis"], out["fixed"], out["alpha"] = unpack_param_grads(buf, n_obj, out["fixed"].shape[0])
-    out["rows"] = (r0, r1)
+    out["rows"] = rows
     return out

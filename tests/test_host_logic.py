@@ -103,6 +103,17 @@ def test_row_blocks_partition_the_grid():
             assert max(sizes) - min(sizes) <= 1
 
 
+def test_cyclic_row_bands_partition_the_grid():
+    for n in (1, 7, 10, 1024, 2048, 8192):
+        for w in (1, 2, 3, 4, 8):
+            parts = [D.row_tiles_cyclic(n, w, r) for r in range(w)]
+            assert sorted(np.concatenate(parts).tolist()) == list(range(n))      # disjoint cover
+            for r, p in enumerate(parts):
+                assert all((int(i) // 8) % w == r for i in p)                    # whole 8-row bands, round robin
+            if n % (8 * w) == 0:
+                assert len({len(p) for p in parts}) == 1                         # equal shares
+
+
 def test_pack_unpack_roundtrip():
     o, ph, f, a = torch.randn(5, 2, 2), torch.randn(5), torch.randn(3, 2), torch.randn(1)
     buf = D.pack_param_grads(o, ph, f, a)
