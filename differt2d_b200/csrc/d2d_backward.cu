@@ -502,7 +502,7 @@ static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out
     size_t smem = ((scene_tab_bytes(p.N) + 15) / 16) * 16;
     if (out.objects_bar || out.phis_bar) smem += (size_t)5 * p.N * sizeof(float);
     auto kern = power_bwd_kernel<MODE, METHOD, TXGRID>;
-    if (smem > 48 * 1024) {
+    if (smem > 32 * 1024) {  // static + dynamic > 48 KB needs the opt-in; the static part is ~8.5 KB
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }

@@ -370,6 +370,33 @@ def test_point_to_point_long_lists_vs_oracle(n_walls, order):
     assert vo.sum() > 0
 
 
+def test_vjp_500_objects_shared_memory_opt_in():
+    """500 objects: the object table (31 KB) plus the backward kernel's cotangent accumulator (10 KB) plus the static
+    driver state (8.5 KB) exceed the 48 KB a launch gets without the opt-in attribute — the launch used to fail with
+    `invalid argument`.  Orders 0-1 over every 8th object (the others only occlude: filter_objects), 3 point-to-point
+    links, hard_sigmoid: value and cotangents vs the autograd oracle."""
+    sc = _random_walls(500)
+    sc = sc.with_transmitters(tx_0=sc.transmitters["tx_0"])
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    grid = np.stack([p.xy for p in sc.receivers.values()])
+    X, Y = grid[:, 0][None, :].copy(), grid[:, 1][None, :].copy()
+    Zbar = np.array([[1.0, -0.5, 2.0]], dtype=np.float32)
+    blocked = tuple(j for j in range(500) if j % 8)
+    with R.clean_gradients():
+        Zo, go = R.power_map_and_vjp(H.oracle_scene_from_product(sc), X, Y, Zbar, max_order=1, filter_nodes=blocked,
+                                     approx=True, alpha=2.0, function="hard_sigmoid")
+    out = F.power_bwd(_cfg("hard_sigmoid", max_order=1, reduce_all=True, filter_nodes=blocked), xys, fixed, grid,
+                      Zbar.reshape(-1), alpha=2.0, device="cuda")
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
+    assert np.abs(out["Z"]).max() > 0
+    _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar")
+    _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar")
+    _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar")
+    _close(out["alpha"], go["alpha"].numpy().reshape(1), 1e-4, "alpha_bar")
+
+
 # ---- FermatPath / MinPath (in-register Adam solver) -----------------------------------------------
 def _vertex_scene():
     """examples/plot_vertex_diffraction_power_map.py:35-38,70-72 — basic_scene, wall 5 replaced by its
