@@ -190,7 +190,7 @@ def bench_reference(args, rank: int, world: int) -> None:
                          "note": "restated reference (JAX unavailable in this image)"},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    _emit(line)
 
 
 def workload_config(args, world):
@@ -244,6 +244,27 @@ def cpu_baseline_sample(sc, args) -> dict:
     return out
 
 
+def _emit(line: dict) -> None:
+    """The ONE JSON line on the real stdout (fd 1 is pointed at stderr while the benchmark runs: NCCL and other
+    native libraries print banners on stdout)."""
+    sys.stdout.flush()
+    if _REAL_STDOUT is not None:
+        os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+    else:
+        print(json.dumps(line), flush=True)
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -257,6 +278,7 @@ def main() -> None:
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
 
+    _quiet_stdout()
     if args.impl == "reference":
         bench_reference(args, rank, world)
         return
@@ -306,7 +328,7 @@ def main() -> None:
     lib = L.lib()
     stream = torch.cuda.current_stream(dev)
     flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(4)] for _ in range(args.steps)]
 
     def step(i=None):
         flush.zero_()
@@ -322,6 +344,8 @@ def main() -> None:
             ev[i][2].record(stream)
         if dist is not None:
             D.allreduce_sum_(pbar)
+            if i is not None:
+                ev[i][3].record(stream)
 
     # FP32 peak (roofline denominator): register-resident FMA chains on every SM, timed alone
     sink = torch.zeros(4, device=dev)
@@ -367,6 +391,13 @@ def main() -> None:
     ms_per_step = elapsed_ms / args.steps
     fwd_ms = float(np.mean([ev[i][0].elapsed_time(ev[i][1]) for i in range(args.steps)]))
     bwd_ms = float(np.mean([ev[i][1].elapsed_time(ev[i][2]) for i in range(args.steps)]))
+    per_rank = None
+    if dist is not None:  # where a multi-GPU step goes, per rank: kernels, all-reduce (incl. waiting for the slowest rank)
+        ar_ms = float(np.mean([ev[i][2].elapsed_time(ev[i][3]) for i in range(args.steps)]))
+        mine = torch.tensor([fwd_ms, bwd_ms, ar_ms], dtype=torch.float64, device=dev)
+        allr = [torch.zeros_like(mine) for _ in range(world)]
+        dist.all_gather(allr, mine)
+        per_rank = [{"fwd_ms": float(t[0]), "bwd_ms": float(t[1]), "allreduce_and_wait_ms": float(t[2])} for t in allr]
 
     # end to end through the host-buffer C ABI entry (pinned host memory in, host memory out)
     grid_p = torch.from_numpy(grid_h).pin_memory()
@@ -445,6 +476,7 @@ def main() -> None:
                 "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "call": "d2d_power_host (fused value+VJP, pinned host buffers in/out, sync)"},
         "gpu_launches": int(launches),
+        "per_rank": per_rank,
         "clocks": clocks,
         "roofline": {
             "bound": "fp32", "kernel": dom, "achieved": kernels[dom]["achieved_tflops"], "peak": peak_tf,
@@ -465,7 +497,7 @@ def main() -> None:
     }
     if world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline_sample(sc, args)
-    print(json.dumps(line), flush=True)
+    _emit(line)
     if dist is not None:
         D.shutdown()
 

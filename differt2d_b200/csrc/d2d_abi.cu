@@ -180,6 +180,9 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
         if (want > 1) k.slices = (int)want;
     }
     if (k.slices > 65535) return fail(D2D_ERR_INVALID_ARGUMENT, "candidate_slices must be <= 65535");
+    // 2-D tiled grids are laid out for thread-block clusters: 8 CTAs = 2 x 4 tiles = one 32 x 32 macro tile whose
+    // candidates are culled once, cooperatively, through distributed shared memory (csrc/d2d_driver.cuh)
+    k.cluster = (k.grid_cols > 0 && k.slices == 1) ? 8 : 0;
     k.mask = p->active_mask;
     k.mask_wpw = (total + 31) / 32;
     return D2D_OK;

@@ -312,14 +312,14 @@ struct BwdAcc {
 
 template <int MODE, int METHOD, int K, bool TXGRID>
 __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
-                                              const float alpha, const float2 fx, const float2 g, const long long col0,
-                                              int& buf, const float zbar, BwdAcc& A, float* s_obj, float* s_phi,
-                                              const uint32_t* mread) {
+                                              const float alpha, const int t, const float2 fx, const float2 g,
+                                              const long long col0, int& buf, const float zbar, BwdAcc& A, float* s_obj,
+                                              float* s_phi, const uint32_t* mread) {
     constexpr int KK = K > 0 ? K : 1;
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
     for_each_candidate<MODE, METHOD, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, mread, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
+        T, p, tile, sh, alpha, t, fx, col0, mread, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
             bool has = false;
             float2 txb = make_float2(0.f, 0.f), rxb = make_float2(0.f, 0.f);
             float ab = 0.f;
@@ -405,6 +405,9 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
     const long long r = tile.r;
     const bool active = tile.active;
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
+    if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
+        if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
+    }
     const float2 g = active ? reinterpret_cast<const float2*>(p.grid)[r] : make_float2(0.f, 0.f);
     float zsum = 0.0f;
     float2 gsum = make_float2(0.f, 0.f);
@@ -425,11 +428,11 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
         long long col0 = 0;
         for (int k = p.min_order; k <= p.max_order; ++k) {
             switch (k) {
-                case 0: run_order_bwd<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
-                case 1: run_order_bwd<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
-                case 2: run_order_bwd<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
-                case 3: run_order_bwd<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
-                case 4: run_order_bwd<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 0: run_order_bwd<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 1: run_order_bwd<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 2: run_order_bwd<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 3: run_order_bwd<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
+                case 4: run_order_bwd<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, zbar, A, s_obj, s_phi, mread); break;
                 default: break;
             }
             col0 += order_count(k, T.n_allowed);
@@ -497,17 +500,18 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
 
 template <int MODE, int METHOD, bool TXGRID>
 static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out, cudaStream_t stream) {
-    const int block = kBlock;
-    const long long nblk = host_tile_blocks(p);
     size_t smem = ((scene_tab_bytes(p.N) + 15) / 16) * 16;
     if (out.objects_bar || out.phis_bar) smem += (size_t)5 * p.N * sizeof(float);
     auto kern = power_bwd_kernel<MODE, METHOD, TXGRID>;
-    if (smem > 32 * 1024) {  // static + dynamic > 48 KB needs the opt-in; the static part is ~8.5 KB
+    if (smem > 32 * 1024) {  // static + dynamic > 48 KB needs the opt-in; the static part is ~11 KB
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<dim3((unsigned)nblk, (unsigned)p.slices), block, smem, stream>>>(p, Zbar, out);
-    return (int)cudaGetLastError();
+    // without an activity mask the backward re-runs the culls: clusters + macro-tile cull as in the forward kernel
+    KParams q = p;
+    q.macro = (host_macro_ok(p) && !p.mask && METHOD == D2D_METHOD_IMAGE && !TXGRID) ? 1 : 0;
+    const cudaError_t e = launch_tiles(kern, q, q.macro != 0, smem, stream, q, Zbar, out);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 #ifndef D2D_TU_MODE

@@ -49,6 +49,8 @@ struct KParams {
     int cull;              // tile-level candidate culling on/off (results are identical either way)
     int slices;            // gridDim.y: CTAs sharing one tile, each walking every slices-th chunk of candidates
     int tile_points;       // grid points per CTA when the tile is 1-D (<= kBlock; 1 for point-to-point links)
+    int cluster;           // 8: 2-D tiles are numbered cluster by cluster (8 CTAs = 2 x 4 tiles = 32 x 32 points); 0: row-major
+    int macro;             // set by a launcher that starts the kernel as clusters of 8 CTAs: macro-tile cull stage on
     int N, T;
     int min_order, max_order;
     int steps;

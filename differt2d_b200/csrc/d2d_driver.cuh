@@ -4,6 +4,16 @@
 // 128 consecutive points otherwise).  For every order k it walks the candidate list in list order
 // (scene.py:166-175) in chunks of one candidate per thread:
 //
+//   0. MACRO CULL (2-D grids; the kernel then runs as thread-block CLUSTERS of 8 CTAs = 2 x 4 tiles = one macro tile
+//      of 32 x 32 points), once, before anything is traced: the cluster's 32 warps split the whole (fixed point,
+//      candidate) list, every thread tests one candidate against the MACRO tile's bounding box with the same
+//      conservative test as step 1, and each warp pushes its ballot — one word of the survivor bitmap — into the
+//      shared memory of all 8 CTAs (distributed shared memory).  After ONE cluster barrier every CTA owns the complete
+//      bitmap and never talks to its neighbours again (no barrier at which a lightly loaded tile would wait for a
+//      heavy one; a first version with per-order survivor lists and two cluster barriers per order lost on the raw
+//      scene what the cull saved).  Steps 1-4 then only see the survivors, enumerated in list order through
+//      per-word prefix counts.  The tile-level test costs ~700 warp instructions per 128 candidates and used to run
+//      on every candidate in every CTA (12 % of the forward kernel on the raw city scene).
 //   1. CULL (one thread = one candidate, integer decode of its index): a conservative, tile-level
 //      necessary condition for a non-zero validity — "some point of the tile's bounding box can have its
 //      last interaction point on the last object" — evaluated from the four corners of the box
@@ -21,9 +31,13 @@
 // The culled work still counts as algorithmic work ("no early-out credit").
 #pragma once
 
+#include <cooperative_groups.h>
+
 #include "d2d_trace.cuh"
 
 namespace d2d {
+
+namespace cg = cooperative_groups;
 
 constexpr int kBlock = 128;
 // resident CTAs per SM the kernels are compiled for (register caps 64 / 96 per thread): occupancy hides the
@@ -36,6 +50,10 @@ constexpr int kBlock = 128;
 #endif
 constexpr int kTileCols = 16;
 constexpr int kTileRows = 8;
+constexpr int kCluster = 8;        // CTAs per cluster = tiles per macro tile
+constexpr int kMacroTilesX = 2;    // macro tile = 2 x 4 tiles = 32 x 32 grid points
+constexpr int kMacroTilesY = 4;
+constexpr int kMacroWords = 512;   // survivor bitmap: up to 16384 (fixed point, candidate) pairs, else no macro stage
 
 // Optional census of the cull (diagnostic builds only: python -m differt2d_b200.build --debug-counters)
 #ifdef D2D_DEBUG_COUNTERS
@@ -49,6 +67,7 @@ struct Tile {
     long long r;      // grid-point index of this thread (row-major), valid when `active`
     bool active;
     float4 bbox;      // xmin, ymin, xmax, ymax over the tile's active points
+    float4 mbox;      // same over the 8 tiles of the cluster (p.macro only)
     float4 wbox;      // same over this thread's warp (inverted / infinite when the warp has no active point)
     float scale;      // max |coordinate| over tile, fixed points and objects (for error bounds)
     float scale_x, scale_y;  // the same per component (lon/lat scenes: |x| ~ 5, |y| ~ 50 — the fp32 lattice differs 8x)
@@ -61,15 +80,49 @@ struct DriverShared {
     int4 list[2][kBlock];    // packed survivors: (c0 | c1 << 16, c2 | c3 << 16, index lo, index hi)
     float4 aux[2][kBlock];   // per survivor: apex (image of the fixed point through all objects) x, y; s-tolerance of
                              // the last interaction for the warp-level test (+inf: no test possible); unused
+    // macro cull (written by all CTAs of the cluster through distributed shared memory)
+    float4 tbox;                             // this tile's bounding box (read by the neighbours)
+    uint32_t mbits[kMacroWords + 1];         // bit (t * C_total + column): the candidate may be valid in the macro tile
+    unsigned short mpref[kMacroWords + 1];   // set bits in the words before word w
 };
 
 // CTAs along x for a problem (host side)
 inline long long host_tile_blocks(const KParams& p) {
     if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
         const long long rows = p.R / p.grid_cols;
-        return (long long)((p.grid_cols + kTileCols - 1) / kTileCols) * ((rows + kTileRows - 1) / kTileRows);
+        const long long tx = (p.grid_cols + kTileCols - 1) / kTileCols, ty = (rows + kTileRows - 1) / kTileRows;
+        if (p.cluster)  // whole macro tiles: CTAs beyond the grid's edge only help with the macro cull
+            return ((tx + kMacroTilesX - 1) / kMacroTilesX) * ((ty + kMacroTilesY - 1) / kMacroTilesY) * kCluster;
+        return tx * ty;
     }
     return (p.R + p.tile_points - 1) / p.tile_points;
+}
+
+// The macro stage needs clusters (2-D tiled grid, no candidate slices) and a bitmap that fits.
+inline bool host_macro_ok(const KParams& p) {
+    const long long bits = (long long)p.T * p.C_total;
+    return p.cluster && p.cull && bits > 0 && bits <= 32LL * kMacroWords;
+}
+
+// Launches a tile kernel: gridDim = (tiles, candidate slices), kBlock threads; as clusters of 8 CTAs when `clusters`.
+template <class... KArgs, class... Args>
+inline cudaError_t launch_tiles(void (*kern)(KArgs...), const KParams& p, const bool clusters, const size_t smem,
+                                cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)host_tile_blocks(p), (unsigned)p.slices, 1);
+    cfg.blockDim = dim3(kBlock, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    if (clusters) {
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = kCluster;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kern, args...);
 }
 
 // Maps (blockIdx, threadIdx) to a grid point; computes the tile's bounding box (all threads must call).
@@ -79,8 +132,15 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
         const long long rows = p.R / p.grid_cols;
         const int tiles_x = (p.grid_cols + kTileCols - 1) / kTileCols;
-        const long long by = blockIdx.x / tiles_x;
-        const int bx = (int)(blockIdx.x % tiles_x);
+        long long by = blockIdx.x / tiles_x;
+        int bx = (int)(blockIdx.x % tiles_x);
+        if (p.cluster) {  // 8 consecutive CTAs (one cluster) = 2 x 4 neighbouring tiles
+            const int macro_x = (tiles_x + kMacroTilesX - 1) / kMacroTilesX;
+            const long long cid = blockIdx.x / kCluster;
+            const int rk = (int)(blockIdx.x % kCluster);
+            bx = kMacroTilesX * (int)(cid % macro_x) + (rk % kMacroTilesX);
+            by = kMacroTilesY * (cid / macro_x) + (rk / kMacroTilesX);
+        }
         const int col = bx * kTileCols + (tid & (kTileCols - 1));
         const long long row = by * kTileRows + (tid / kTileCols);
         t.active = col < p.grid_cols && row < rows;
@@ -113,6 +173,20 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     xmax = fmaxf(fmaxf(sh.red[0][2], sh.red[1][2]), fmaxf(sh.red[2][2], sh.red[3][2]));
     ymax = fmaxf(fmaxf(sh.red[0][3], sh.red[1][3]), fmaxf(sh.red[2][3], sh.red[3][3]));
     t.bbox = make_float4(xmin, ymin, xmax, ymax);
+    t.mbox = t.bbox;
+    if (p.macro) {  // bounding box of the cluster's 8 tiles (empty tiles hold inverted boxes)
+        cg::cluster_group cl = cg::this_cluster();
+        if (tid == 0) sh.tbox = t.bbox;
+        cl.sync();
+#pragma unroll
+        for (int r = 0; r < kCluster; ++r) {
+            const float4 b = *cl.map_shared_rank(&sh.tbox, r);
+            xmin = fminf(xmin, b.x); ymin = fminf(ymin, b.y);
+            xmax = fmaxf(xmax, b.z); ymax = fmaxf(ymax, b.w);
+        }
+        t.mbox = make_float4(xmin, ymin, xmax, ymax);
+        cl.sync();  // nobody leaves (or reuses tbox) while a neighbour may still read it
+    }
     float sx = fmaxf(fabsf(xmin), fabsf(xmax)), sy = fmaxf(fabsf(ymin), fabsf(ymax));
     if (!(sx < CUDART_INF_F)) sx = 0.0f;  // empty tile
     if (!(sy < CUDART_INF_F)) sy = 0.0f;
@@ -153,12 +227,15 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
 //       provably longer than Lmin.
 // Error bound of s (first order, eps = 2^-24, S = largest coordinate magnitude in play).  Differences of
 // fp32 inputs carry RELATIVE errors (u, v exact up to eps|u|, eps|v|), the only absolute term is the final
-// rounding of X onto the fp32 lattice, eps (S + |g||u|):
+// rounding of X onto the fp32 lattice, half an ulp of its binade: eps 2^floor(log2(S + |g||u|)) <= eps (S + |g||u|):
 //     dX_c <= eps [S + |g||u| + 4|g||u_c| + 4.4 (|u_c|/|un|)(|v|_1 + |g||u|_1)] + L dev
 //     ds   <= (|t_x| dX_x + |t_y| dX_y)/tt + 4 eps |s|
 // with L = (1 + |g|)(1 + |u|/|un|) the Lipschitz constant of p -> X and dev the distance of the thread's
 // computed p from the convex set used here.  tol = 2.5 ds + 1e-6 covers both the threads' evaluation and the
 // (FMA-contracted) evaluation at the extreme points.
+// largest power of two <= x (x > 0, normal)
+__device__ __forceinline__ float pow2_floor(const float x) { return __int_as_float(__float_as_int(x) & 0x7f800000); }
+
 template <int K>
 __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (&c)[K > 0 ? K : 1],
                                                   const float2 (&I)[K + 1], const float4 bbox, const float scale,
@@ -231,9 +308,11 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         const float lip = (1.0f + gabs) * (1.0f + u2m * run);
         const float amp = 4.4f * (V1 + gabs * U1) * run;
         const float gu5 = 5.0f * gabs * u2m;  // (4 of the 5: the approximate quotient g at the extreme points)
-        // lattice rounding of X per component: |X_c| <= S_c + |g||u|
-        const float dXx = eps * (scale_x + gu5 + 4.0f * gabs * uxm + amp * uxm) + 1.5f * lip * dev;
-        const float dXy = eps * (scale_y + gu5 + 4.0f * gabs * uym + amp * uym) + 1.5f * lip * dev;
+        // lattice rounding of X per component: |X_c| <= S_c + |g||u|, and rounding a value of that binade moves it by
+        // at most half an ulp = 2^-24 * 2^floor(log2 |X_c|) (not 2^-24 |X_c|: up to 2x tighter, 1.6x at latitude 50.7)
+        const float gu1 = gabs * u2m;
+        const float dXx = eps * (pow2_floor(scale_x + gu1) + 0.8f * gu5 + 4.0f * gabs * uxm + amp * uxm) + 1.5f * lip * dev;
+        const float dXy = eps * (pow2_floor(scale_y + gu1) + 0.8f * gu5 + 4.0f * gabs * uym + amp * uym) + 1.5f * lip * dev;
         const float smag = fmaxf(fabsf(smin), fabsf(smax));
         const float ds = (fabsf(w0.z) * dXx + fabsf(w0.w) * dXy) * (rtt * 1.000001f) + 8.0f * eps * smag;
         const float tol = 2.5f * ds + 1e-6f;
@@ -323,6 +402,60 @@ __device__ __forceinline__ bool warp_may_be_valid(const float4 w0, const float4 
     return !(smax < xz - tol || smin > 1.0f - xz + tol);
 }
 
+// One candidate, out of line (ONE copy of the decode + image chain + tile test per order in a translation unit: the
+// macro stage and the tile stage both call it, and these kernels are instruction-fetch bound).
+struct CandTest {
+    int c01, c23;     // objects, 16 bits each
+    float2 apex;      // image of the fixed point through all objects (ImagePath on a receivers grid)
+    float tol_last;   // error bound of the last interaction's s (+inf: none)
+    bool keep;
+};
+
+template <int K>
+__device__ __noinline__ CandTest test_candidate(unsigned char* smem, const int N, const int m, const long long idx,
+                                                const float2 fx, const bool apex_wanted, const bool cull,
+                                                const float4 box, const float scale, const float scale_x,
+                                                const float scale_y, const float xz, const float loss_dead) {
+    constexpr int KK = K > 0 ? K : 1;
+    const SceneTab T = carve_tab(smem, N);
+    CandTest o;
+    o.apex = fx;
+    o.tol_last = CUDART_INF_F;
+    o.keep = true;
+    // index -> positions in `allowed` (lexicographic, no equal neighbours)
+    int c[KK];
+    long long rem = idx;
+    int dig[KK];
+#pragma unroll
+    for (int i = K - 1; i >= 1; --i) {
+        dig[i] = (int)(rem % (m - 1));
+        rem /= (m - 1);
+    }
+    dig[0] = (int)rem;
+    int prev = -1;
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        int pos = dig[i];
+        if (i > 0 && pos >= prev) ++pos;
+        c[i] = T.allowed[pos];
+        prev = pos;
+    }
+    o.c01 = c[0] | ((K > 1 ? c[K > 1 ? 1 : 0] : 0) << 16);
+    o.c23 = (K > 2 ? c[K > 2 ? 2 : 0] : 0) | ((K > 3 ? c[K > 3 ? 3 : 0] : 0) << 16);
+    if (apex_wanted) {
+        float2 I[K + 1];
+        I[0] = fx;
+#pragma unroll
+        for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[c[i]], T.w1[c[i]]);
+        o.apex = I[K];
+        if (cull) {
+            D2D_COUNT(0);
+            o.keep = tile_may_be_valid<K>(T, c, I, box, scale, scale_x, scale_y, xz, loss_dead, o.tol_last);
+        }
+    }
+    return o;
+}
+
 // number of candidates of order K over m visitable objects
 __device__ __forceinline__ long long order_count(const int K, const int m) {
     if (K == 0) return 1;
@@ -332,16 +465,82 @@ __device__ __forceinline__ long long order_count(const int K, const int m) {
     return c;
 }
 
+// Macro stage (p.macro: the kernel runs as clusters of 8 CTAs): the survivor bitmap of the cluster's macro tile, built
+// cooperatively and pushed into every CTA's shared memory; must be called by every thread of every CTA, once, after
+// make_tile().  Word wd of the bitmap is the ballot of one warp over the pairs 32 wd ... 32 wd + 31, pair b = fixed point
+// b / C_total, candidate column b % C_total (orders ascending, list order inside an order).
+template <int MODE>
+__device__ __forceinline__ void macro_prologue(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
+                                               const float alpha) {
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank();
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const long long Ct = p.C_total, nbits = (long long)p.T * Ct;
+    const int nwords = (int)((nbits + 31) >> 5);
+    const float xz = x_zero<MODE>(alpha);
+    const int m = T.n_allowed;
+    unsigned char* const smem_tab = reinterpret_cast<unsigned char*>(T.w0);
+#pragma unroll 1
+    for (int wd = rank * (kBlock / 32) + warp; wd < nwords; wd += kCluster * (kBlock / 32)) {
+        const long long b = ((long long)wd << 5) + lane;
+        bool k = false;
+        if (b < nbits) {
+            const int t = (int)(b / Ct);
+            long long col = b - (long long)t * Ct;
+            const float2 fx = reinterpret_cast<const float2*>(p.fixed)[t];
+            int ord = p.min_order;
+            for (; ord < p.max_order; ++ord) {  // order of column `col`
+                const long long c = order_count(ord, m);
+                if (col < c) break;
+                col -= c;
+            }
+            D2D_COUNT(20);
+            const float ld = p.tol - xz;
+            switch (ord) {
+                case 1: k = test_candidate<1>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
+                case 2: k = test_candidate<2>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
+                case 3: k = test_candidate<3>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
+                case 4: k = test_candidate<4>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
+                default: k = true; break;  // order 0: line of sight, never culled
+            }
+            if (k) D2D_COUNT(21);
+        }
+        const unsigned word = __ballot_sync(0xffffffffu, k);
+        if (lane < kCluster) cl.map_shared_rank(&sh.mbits[0], lane)[wd] = word;  // one copy per CTA of the cluster
+    }
+    cl.sync();  // the bitmap is complete in every CTA; no remote access after this point
+    if (warp == 0) {  // set bits before each word
+        int run = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int c = (w0 + lane < nwords) ? __popc(sh.mbits[w0 + lane]) : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (w0 + lane < nwords) sh.mpref[w0 + lane] = (unsigned short)(run + inc - c);
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            sh.mpref[nwords] = (unsigned short)run;
+            sh.mbits[nwords] = 0u;
+        }
+    }
+    __syncthreads();
+}
+
 // Walks all candidates of order K for the fixed point `fx`; calls visit(cd, col, apex) — uniformly over a
 // WARP — for every candidate that survives the tile and warp culls, in list order.  `col0` = column of the first
 // candidate of this order in the global list; `apex` = image of fx through the candidate's objects (ImagePath on a
 // receivers grid only, otherwise unspecified).
+// `t` = index of the fixed point (rows of the macro bitmap).
 // `mread` (backward kernel after a forward that wrote the activity mask): rows of this CTA's four warps for the
 // current fixed point; the stored bits then REPLACE both culls — only candidates some warp of the CTA found
 // valid are decoded, and each warp only visits its own set bits.
 template <int MODE, int METHOD, int K, bool TXGRID, class Visit>
 __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KParams& p, const Tile& tile,
-                                                   DriverShared& sh, const float alpha, const float2 fx,
+                                                   DriverShared& sh, const float alpha, const int t, const float2 fx,
                                                    const long long col0, const uint32_t* __restrict__ mread, int& buf,
                                                    Visit&& visit) {
     const int m = T.n_allowed;
@@ -359,62 +558,32 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     const long long wpw = p.mask_wpw;
     const float xz = x_zero<MODE>(alpha);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    // candidate slices (point-to-point links with huge candidate lists): CTA y walks chunks y, y + slices, ...
-    for (long long base = (long long)blockIdx.y * kBlock; base < Ck; base += (long long)kBlock * gridDim.y) {
-        const long long idx = base + tid;
-        bool keep = false;
-        float2 apex = fx;
-        float tol_last = CUDART_INF_F;
-        int c[KK];
-#pragma unroll
-        for (int i = 0; i < KK; ++i) c[i] = 0;
-        bool pre = idx < Ck;
+
+    unsigned char* const smem_tab = reinterpret_cast<unsigned char*>(T.w0);  // (the table starts with w0: carve_tab)
+
+    // One chunk of at most kBlock candidates, one per thread (`pre` = this thread has one), in list order across the
+    // CTA: tile cull, ordered compaction, warp cull, visits.  Must be called by every thread of the CTA.
+    auto chunk = [&](const long long idx, bool pre) {
+        CandTest ct;
+        ct.c01 = ct.c23 = 0;
+        ct.apex = fx;
+        ct.tol_last = CUDART_INF_F;
+        ct.keep = false;
         if (pre && mread) {
             const long long wd = (col0 + idx) >> 5;
             const uint32_t any4 = mread[wd] | mread[wpw + wd] | mread[2 * wpw + wd] | mread[3 * wpw + wd];
             pre = (any4 >> ((col0 + idx) & 31)) & 1u;
         }
-        if (pre) {
-            // index -> positions in `allowed` (lexicographic, no equal neighbours)
-            long long rem = idx;
-            int dig[KK];
-#pragma unroll
-            for (int i = K - 1; i >= 1; --i) {
-                dig[i] = (int)(rem % (m - 1));
-                rem /= (m - 1);
-            }
-            dig[0] = (int)rem;
-            int prev = -1;
-#pragma unroll
-            for (int i = 0; i < K; ++i) {
-                int pos = dig[i];
-                if (i > 0 && pos >= prev) ++pos;
-                c[i] = T.allowed[pos];
-                prev = pos;
-            }
-            keep = true;
-            if (kApex) {
-                float2 I[K + 1];
-                I[0] = fx;
-#pragma unroll
-                for (int i = 0; i < K; ++i) I[i + 1] = mirror(I[i], T.w0[c[i]], T.w1[c[i]]);
-                apex = I[K];
-                if (cull) {
-                    D2D_COUNT(0);
-                    keep = tile_may_be_valid<K>(T, c, I, tile.bbox, tile.scale, tile.scale_x, tile.scale_y, xz, p.tol - xz,
-                                                tol_last);
-                }
-            }
-        }
+        if (pre)
+            ct = test_candidate<K>(smem_tab, p.N, m, idx, fx, kApex, cull, tile.bbox, tile.scale, tile.scale_x,
+                                   tile.scale_y, xz, p.tol - xz);
+        const bool keep = ct.keep;
         // ordered compaction: per-warp segments keep list order
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
         if (keep) {
             const int off = __popc(ballot & ((1u << lane) - 1u));
-            sh.list[buf][warp * 32 + off] =
-                make_int4(c[0] | ((K > 1 ? c[K > 1 ? 1 : 0] : 0) << 16),
-                          (K > 2 ? c[K > 2 ? 2 : 0] : 0) | ((K > 3 ? c[K > 3 ? 3 : 0] : 0) << 16),
-                          (int)(idx & 0xffffffffLL), (int)(idx >> 32));
-            if (kApex) sh.aux[buf][warp * 32 + off] = make_float4(apex.x, apex.y, tol_last, 0.f);
+            sh.list[buf][warp * 32 + off] = make_int4(ct.c01, ct.c23, (int)(idx & 0xffffffffLL), (int)(idx >> 32));
+            if (kApex) sh.aux[buf][warp * 32 + off] = make_float4(ct.apex.x, ct.apex.y, ct.tol_last, 0.f);
         }
         if (lane == 0) sh.wcount[buf][warp] = __popc(ballot);
         __syncthreads();
@@ -476,6 +645,40 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
             }
         }
         buf ^= 1;  // the next chunk fills the other buffer: one barrier per chunk
+    };
+
+    // With a macro bitmap (macro_prologue) the chunk loop walks the survivors of this (fixed point, order) only: the
+    // g-th set bit of the range [B0, B0 + Ck), found through the per-word prefix counts.  (ONE loop serves both forms,
+    // so that chunk() — and with it the whole trace — is instantiated once.)
+    const bool use_macro = cull && p.macro;  // uniform over the cluster
+    const long long B0 = (long long)t * p.C_total + col0;
+    auto set_before = [&](const long long b) {  // set bits of the bitmap below bit b
+        const int w = (int)(b >> 5);
+        return (int)sh.mpref[w] + __popc(sh.mbits[w] & ((1u << (b & 31)) - 1u));
+    };
+    long long G = Ck;  // length of the list the chunk loop walks
+    int r0 = 0;
+    if (use_macro) {
+        r0 = set_before(B0);
+        G = (tile.bbox.x <= tile.bbox.z) ? set_before(B0 + Ck) - r0 : 0;  // (a CTA beyond the grid's edge traces nothing)
+    }
+    // candidate slices (point-to-point links with huge candidate lists): CTA y walks chunks y, y + slices, ...
+#pragma unroll 1
+    for (long long g0 = (long long)blockIdx.y * kBlock; g0 < G; g0 += (long long)kBlock * gridDim.y) {
+        const long long g = g0 + tid;
+        long long idx = g;
+        if (use_macro && g < G) {
+            const int target = r0 + (int)g;
+            int lo = (int)(B0 >> 5), hi = (int)((B0 + Ck - 1) >> 5);
+            while (lo < hi) {  // first word whose cumulative count exceeds the target
+                const int mid = (lo + hi) >> 1;
+                if ((int)sh.mpref[mid + 1] > target) hi = mid;
+                else lo = mid + 1;
+            }
+            const unsigned bit = __fns(sh.mbits[lo], 0u, target - (int)sh.mpref[lo] + 1);
+            idx = (((long long)lo << 5) + bit) - B0;
+        }
+        chunk(idx, g < G);
     }
 }
 

@@ -14,12 +14,12 @@ namespace d2d {
 
 template <int MODE, int METHOD, int K, bool TXGRID>
 __device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
-                                          const float alpha, const float2 fx, const float2 g, const long long col0,
-                                          int& buf, float& acc, float* vrow, uint32_t* mrow) {
+                                          const float alpha, const int t, const float2 fx, const float2 g,
+                                          const long long col0, int& buf, float& acc, float* vrow, uint32_t* mrow) {
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
     for_each_candidate<MODE, METHOD, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, nullptr, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
+        T, p, tile, sh, alpha, t, fx, col0, nullptr, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
             float2 X[K + 2];
             float valid = 0.0f;
             if (tile.active) {
@@ -63,6 +63,9 @@ __global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(con
     build_tab(T, p, &sh.count);
     const Tile tile = make_tile(p, T, sh);
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
+    if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
+        if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
+    }
     const float2 g = tile.active ? reinterpret_cast<const float2*>(p.grid)[tile.r] : make_float2(0.f, 0.f);
     float zsum = 0.0f;
     int buf = 0;
@@ -76,11 +79,11 @@ __global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(con
                                 : nullptr;
         for (int k = p.min_order; k <= p.max_order; ++k) {
             switch (k) {
-                case 0: run_order<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
-                case 1: run_order<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
-                case 2: run_order<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
-                case 3: run_order<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
-                case 4: run_order<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 0: run_order<MODE, METHOD, 0, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 1: run_order<MODE, METHOD, 1, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 2: run_order<MODE, METHOD, 2, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 3: run_order<MODE, METHOD, 3, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, acc, vrow, mrow); break;
+                case 4: run_order<MODE, METHOD, 4, TXGRID>(T, p, tile, sh, alpha, t, fx, g, col0, buf, acc, vrow, mrow); break;
                 default: break;
             }
             col0 += order_count(k, T.n_allowed);
@@ -99,15 +102,17 @@ __global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(con
 
 template <int MODE, int METHOD, bool TXGRID>
 static int launch_one(const KParams& p, float* Z, float* valid_out, cudaStream_t stream) {
-    const long long nblk = host_tile_blocks(p);
     const size_t smem = scene_tab_bytes(p.N);
     auto kern = power_fwd_kernel<MODE, METHOD, TXGRID>;
-    if (smem > 32 * 1024) {  // static + dynamic > 48 KB needs the opt-in; the static part is ~8.5 KB
+    if (smem > 32 * 1024) {  // static + dynamic > 48 KB needs the opt-in; the static part is ~11 KB
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<dim3((unsigned)nblk, (unsigned)p.slices), kBlock, smem, stream>>>(p, Z, valid_out);
-    return (int)cudaGetLastError();
+    // thread-block clusters (macro-tile cull through distributed shared memory) where there is something to cull
+    KParams q = p;
+    q.macro = (host_macro_ok(p) && METHOD == D2D_METHOD_IMAGE && !TXGRID) ? 1 : 0;
+    const cudaError_t e = launch_tiles(kern, q, q.macro != 0, smem, stream, q, Z, valid_out);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 template <int MODE, int METHOD>

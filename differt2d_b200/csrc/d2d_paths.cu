@@ -24,7 +24,7 @@ __device__ __forceinline__ void run_order_paths(const SceneTab& T, const KParams
     const float2 tx = TXGRID ? g : fx;
     const float2 rx = TXGRID ? fx : g;
     for_each_candidate<MODE, METHOD, K, TXGRID>(
-        T, p, tile, sh, alpha, fx, col0, nullptr, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
+        T, p, tile, sh, alpha, t, fx, col0, nullptr, buf, [&](const Cand<K>& cd, const long long col, const float2 apex) {
             if (!tile.active) return;
             float2 X[K + 2];
             float valid, loss = 0.0f;
@@ -76,6 +76,9 @@ __global__ void __launch_bounds__(kBlock) paths_kernel(const KParams p, const Pa
     build_tab(T, p, &sh.count);
     const Tile tile = make_tile(p, T, sh);
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
+    if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
+        if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
+    }
     const float2 g = tile.active ? reinterpret_cast<const float2*>(p.grid)[tile.r] : make_float2(0.f, 0.f);
     int buf = 0;
     for (int t = 0; t < p.T; ++t) {
@@ -97,15 +100,16 @@ __global__ void __launch_bounds__(kBlock) paths_kernel(const KParams p, const Pa
 
 template <int MODE, int METHOD, bool TXGRID>
 static int launch_paths_one(const KParams& p, const PathsOut& out, cudaStream_t stream) {
-    const long long nblk = host_tile_blocks(p);
     const size_t smem = scene_tab_bytes(p.N);
     auto kern = paths_kernel<MODE, METHOD, TXGRID>;
-    if (smem > 32 * 1024) {  // static + dynamic > 48 KB needs the opt-in; the static part is ~8.5 KB
+    if (smem > 32 * 1024) {  // static + dynamic > 48 KB needs the opt-in; the static part is ~11 KB
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return (int)e;
     }
-    kern<<<dim3((unsigned)nblk, (unsigned)p.slices), kBlock, smem, stream>>>(p, out);
-    return (int)cudaGetLastError();
+    KParams q = p;
+    q.macro = (host_macro_ok(p) && METHOD == D2D_METHOD_IMAGE && !TXGRID) ? 1 : 0;
+    const cudaError_t e = launch_tiles(kern, q, q.macro != 0, smem, stream, q, out);
+    return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }
 
 template <int MODE, int METHOD>
