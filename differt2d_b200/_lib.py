@@ -21,6 +21,7 @@ KIND_WALL, KIND_RIS, KIND_VERTEX = 0, 1, 2
 GRID_RECEIVERS, GRID_TRANSMITTERS = 0, 1
 METHOD_IMAGE, METHOD_FERMAT, METHOD_MINPATH = 0, 1, 2
 MODE_HARD, MODE_HARD_SIGMOID, MODE_SIGMOID = 0, 1, 2
+GRAD_CLEAN, GRAD_NAN_PARITY = 0, 1
 FUN_RECEIVED_POWER, FUN_LENGTH_SQUARED = 0, 1
 
 

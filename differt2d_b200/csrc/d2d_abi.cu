@@ -126,7 +126,10 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
         return fail(D2D_ERR_INVALID_ARGUMENT, "alpha must be > 0 (activations must be non-decreasing)");
     if (p->method != D2D_METHOD_IMAGE && p->steps < 1)
         return fail(D2D_ERR_INVALID_ARGUMENT, "steps must be >= 1 (optimize.py:96 indexes losses[-1])");
-    if (p->grad_mode != D2D_GRAD_CLEAN) return fail(D2D_ERR_UNSUPPORTED, "only D2D_GRAD_CLEAN is implemented");
+    if (p->grad_mode != D2D_GRAD_CLEAN && p->grad_mode != D2D_GRAD_NAN_PARITY)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "bad grad_mode");
+    if (p->grad_mode == D2D_GRAD_NAN_PARITY && p->method != D2D_METHOD_IMAGE)
+        return fail(D2D_ERR_UNSUPPORTED, "D2D_GRAD_NAN_PARITY covers ImagePath only");
     std::memset(&k, 0, sizeof(k));
     k.xys = p->objects_xys;
     k.kinds = p->object_kinds;
@@ -310,7 +313,12 @@ int d2d_power_bwd(const D2DProblem* p, const float* Zbar, float* Z_out, float* g
         return fail(D2D_ERR_INVALID_ARGUMENT, "Fermat/MinPath need x0 (initial guesses per candidate)");
     d2d::BwdOut out{Z_out, grid_bar, objects_bar, phis_bar, fixed_bar, alpha_bar};
     long long n = 0;
-    const int e = d2d::launch_power_bwd(k, p->mode, p->grid_role, p->method, Zbar, out, (cudaStream_t)stream, &n);
+    int e = d2d::launch_power_bwd(k, p->mode, p->grid_role, p->method, Zbar, out, (cudaStream_t)stream, &n);
+    if (e == 0 && p->grad_mode == D2D_GRAD_NAN_PARITY) {
+        if (k.C_total > (1LL << 22))
+            return fail(D2D_ERR_UNSUPPORTED, "D2D_GRAD_NAN_PARITY visits every candidate per grid point: lists up to 2^22");
+        e = d2d::launch_nan_poison(k, p->mode, p->grid_role, out, (cudaStream_t)stream, &n);
+    }
     g_launches += n;
     return e == 0 ? D2D_OK : cuda_fail(e, "power_bwd_kernel");
 }

@@ -408,6 +408,7 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
     if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
         if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
     }
+    if (p.mask && mask_bitmap_fits(p)) mask_prologue(p, sh);
     const float2 g = active ? reinterpret_cast<const float2*>(p.grid)[r] : make_float2(0.f, 0.f);
     float zsum = 0.0f;
     float2 gsum = make_float2(0.f, 0.f);

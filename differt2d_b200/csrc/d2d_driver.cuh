@@ -465,6 +465,30 @@ __device__ __forceinline__ long long order_count(const int K, const int m) {
     return c;
 }
 
+// set bits before each word of sh.mbits[0 .. nwords) -> sh.mpref (warp 0; every thread of the CTA must call)
+__device__ __forceinline__ void bitmap_prefix(DriverShared& sh, const int nwords) {
+    const int lane = threadIdx.x & 31;
+    if ((threadIdx.x >> 5) == 0) {
+        int run = 0;
+        for (int w0 = 0; w0 < nwords; w0 += 32) {
+            const int c = (w0 + lane < nwords) ? __popc(sh.mbits[w0 + lane]) : 0;
+            int inc = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += v;
+            }
+            if (w0 + lane < nwords) sh.mpref[w0 + lane] = (unsigned short)(run + inc - c);
+            run += __shfl_sync(0xffffffffu, inc, 31);
+        }
+        if (lane == 0) {
+            sh.mpref[nwords] = (unsigned short)run;
+            sh.mbits[nwords] = 0u;
+        }
+    }
+    __syncthreads();
+}
+
 // Macro stage (p.macro: the kernel runs as clusters of 8 CTAs): the survivor bitmap of the cluster's macro tile, built
 // cooperatively and pushed into every CTA's shared memory; must be called by every thread of every CTA, once, after
 // make_tile().  Word wd of the bitmap is the ballot of one warp over the pairs 32 wd ... 32 wd + 31, pair b = fixed point
@@ -509,25 +533,23 @@ __device__ __forceinline__ void macro_prologue(const SceneTab& T, const KParams&
         if (lane < kCluster) cl.map_shared_rank(&sh.mbits[0], lane)[wd] = word;  // one copy per CTA of the cluster
     }
     cl.sync();  // the bitmap is complete in every CTA; no remote access after this point
-    if (warp == 0) {  // set bits before each word
-        int run = 0;
-        for (int w0 = 0; w0 < nwords; w0 += 32) {
-            const int c = (w0 + lane < nwords) ? __popc(sh.mbits[w0 + lane]) : 0;
-            int inc = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += v;
-            }
-            if (w0 + lane < nwords) sh.mpref[w0 + lane] = (unsigned short)(run + inc - c);
-            run += __shfl_sync(0xffffffffu, inc, 31);
-        }
-        if (lane == 0) {
-            sh.mpref[nwords] = (unsigned short)run;
-            sh.mbits[nwords] = 0u;
-        }
+    bitmap_prefix(sh, nwords);
+}
+
+// Backward kernel after a forward that wrote the activity mask: the same bitmap, filled from the mask rows of this CTA's
+// four warps (bit = some lane of the CTA found the candidate valid), so that the chunk loop walks the handful of marked
+// candidates instead of testing every column of the list.  Rows are word aligned: bit (t * 32 wpw + column).
+__device__ __forceinline__ bool mask_bitmap_fits(const KParams& p) { return (long long)p.T * p.mask_wpw <= kMacroWords; }
+
+__device__ __forceinline__ void mask_prologue(const KParams& p, DriverShared& sh) {
+    const int wpw = (int)p.mask_wpw, nwords = p.T * wpw;
+    for (int w = threadIdx.x; w < nwords; w += kBlock) {
+        const int t = w / wpw, ww = w - t * wpw;
+        const uint32_t* row = p.mask + ((long long)t * gridDim.x * (kBlock / 32) + (long long)blockIdx.x * (kBlock / 32)) * wpw + ww;
+        sh.mbits[w] = row[0] | row[wpw] | row[2 * wpw] | row[3 * wpw];
     }
     __syncthreads();
+    bitmap_prefix(sh, nwords);
 }
 
 // Walks all candidates of order K for the fixed point `fx`; calls visit(cd, col, apex) — uniformly over a
@@ -560,6 +582,8 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
     unsigned char* const smem_tab = reinterpret_cast<unsigned char*>(T.w0);  // (the table starts with w0: carve_tab)
+    // a survivor bitmap (macro cull, or the activity mask in the backward kernel) replaces the walk over all columns
+    const bool use_macro = (cull && p.macro) || (mread && mask_bitmap_fits(p));  // uniform over the CTA
 
     // One chunk of at most kBlock candidates, one per thread (`pre` = this thread has one), in list order across the
     // CTA: tile cull, ordered compaction, warp cull, visits.  Must be called by every thread of the CTA.
@@ -569,7 +593,7 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
         ct.apex = fx;
         ct.tol_last = CUDART_INF_F;
         ct.keep = false;
-        if (pre && mread) {
+        if (pre && mread && !use_macro) {
             const long long wd = (col0 + idx) >> 5;
             const uint32_t any4 = mread[wd] | mread[wpw + wd] | mread[2 * wpw + wd] | mread[3 * wpw + wd];
             pre = (any4 >> ((col0 + idx) & 31)) & 1u;
@@ -647,11 +671,10 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
         buf ^= 1;  // the next chunk fills the other buffer: one barrier per chunk
     };
 
-    // With a macro bitmap (macro_prologue) the chunk loop walks the survivors of this (fixed point, order) only: the
+    // With a bitmap (macro_prologue / mask_prologue) the chunk loop walks the survivors of this (fixed point, order) only: the
     // g-th set bit of the range [B0, B0 + Ck), found through the per-word prefix counts.  (ONE loop serves both forms,
     // so that chunk() — and with it the whole trace — is instantiated once.)
-    const bool use_macro = cull && p.macro;  // uniform over the cluster
-    const long long B0 = (long long)t * p.C_total + col0;
+    const long long B0 = (long long)t * (mread ? 32 * wpw : p.C_total) + col0;
     auto set_before = [&](const long long b) {  // set bits of the bitmap below bit b
         const int w = (int)(b >> 5);
         return (int)sh.mpref[w] + __popc(sh.mbits[w] & ((1u << (b & 31)) - 1u));

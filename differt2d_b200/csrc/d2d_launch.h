@@ -38,6 +38,10 @@ int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, floa
 int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, const float* Zbar, const BwdOut& out,
                      cudaStream_t stream, long long* launches);
 
+// D2D_GRAD_NAN_PARITY: overwrites with NaN the cotangents the reference's literal graph poisons (d2d_nan.cu)
+int launch_nan_poison(const KParams& p, int mode, int grid_role, const BwdOut& out, cudaStream_t stream,
+                      long long* launches);
+
 // One translation unit per logic mode (compiled from the same source with -DD2D_TU_MODE=<mode>, in parallel).
 template <int MODE>
 int launch_fwd_mode(const KParams& p, int grid_role, int method, float* Z, float* valid_out, cudaStream_t s);

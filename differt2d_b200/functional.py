@@ -20,6 +20,7 @@ MODES = {"hard": L.MODE_HARD, "hard_sigmoid": L.MODE_HARD_SIGMOID, "sigmoid": L.
 METHODS = {"image": L.METHOD_IMAGE, "fermat": L.METHOD_FERMAT, "minpath": L.METHOD_MINPATH}
 FUNS = {"received_power": L.FUN_RECEIVED_POWER, "length_squared": L.FUN_LENGTH_SQUARED}
 ROLES = {"receivers": L.GRID_RECEIVERS, "transmitters": L.GRID_TRANSMITTERS}
+GRAD_MODES = {"clean": L.GRAD_CLEAN, "nan_parity": L.GRAD_NAN_PARITY}
 
 
 @dataclass(frozen=True)
@@ -44,6 +45,9 @@ class TraceConfig:
     grid_cols: int = 0  # row length of a row-major mesh grid (enables 16 x 8 tiles); 0 = unknown
     cull: bool = True   # tile-level candidate culling (identical results)
     candidate_slices: int = 0  # 0 = automatic; > 1 splits each tile's candidate list over that many CTAs
+    # "clean": masked branches have zero cotangent.  "nan_parity": additionally NaN wherever jax.grad over the
+    # reference's literal graph yields NaN (geometry.py:1105, :227-230, :163-171) — ImagePath only, diagnostic speed
+    grad_mode: str = "clean"
 
 
 def _dev_f32(x, device) -> torch.Tensor:
@@ -112,6 +116,7 @@ class _Packed:
         p.grid_cols = int(cfg.grid_cols)
         p.no_cull = 0 if cfg.cull else 1
         p.candidate_slices = int(cfg.candidate_slices)
+        p.grad_mode = GRAD_MODES[cfg.grad_mode]
         self.p = p
         self.T = self.fixed.shape[0]
         self.R = self.grid.shape[0]

@@ -57,6 +57,10 @@ extern "C" {
 
 /* gradient semantics of masked branches (DESIGN.md "NaN semantics") */
 #define D2D_GRAD_CLEAN 0 /* masked / saturated branches have zero cotangent */
+#define D2D_GRAD_NAN_PARITY 1 /* the clean gradient, then NaN wherever jax.grad over the reference's literal graph    */
+                              /* yields NaN (geometry.py:1105 single `where`, :227-230 normalize(0), :163-171 alpha *  */
+                              /* inf): ImagePath only, every candidate visited without culling (diagnostic mode;       */
+                              /* csrc/d2d_nan.cu)                                                                      */
 
 #define D2D_OK 0
 #define D2D_ERR_INVALID_ARGUMENT 1

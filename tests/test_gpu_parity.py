@@ -161,6 +161,52 @@ def test_vjp_against_autograd_oracle(name, mode, alpha, generic):
         assert out["alpha"][0] == 0.0
 
 
+@pytest.mark.parametrize("case", ["obstacle_regular", "square_regular", "geojson_norm", "basic_generic"])
+@pytest.mark.parametrize("mode,alpha", [("hard", 100.0), ("hard_sigmoid", 20.0), ("sigmoid", 10.0)])
+def test_nan_parity_gradient_mode(case, mode, alpha):
+    """grad_mode="nan_parity": NaN exactly where reverse mode over the reference's LITERAL graph (the oracle without
+    clean_gradients: single `where` at geometry.py:1105, normalize(0) at :227-230, alpha * inf at :163-171) yields NaN,
+    the clean cotangent everywhere else.  Regular grids on the axis-aligned canned scenes hit un == 0 and d == 0 on
+    whole rows; the geojson scene's zero-length closure walls poison everything; a generic scene stays NaN-free."""
+    if case == "obstacle_regular" or case == "square_regular":
+        sc = SCENES["obstacle" if case == "obstacle_regular" else "square"]
+        X, Y = np.meshgrid(np.linspace(0, 1, 9, dtype=np.float32), np.linspace(0, 1, 11, dtype=np.float32))
+    elif case == "geojson_norm":
+        sc = SCENES["geojson_norm"]
+        X, Y = H.jittered_grid(sc, 4, 5, seed=2)
+    else:
+        sc = H.generic_position(SCENES["basic"])
+        X, Y = H.jittered_grid(sc, 5, 6, seed=2)
+    osc = H.oracle_scene_from_product(sc)
+    Zbar = np.random.default_rng(3).standard_normal(X.shape).astype(np.float32)
+    Zo, go = R.power_map_and_vjp(osc, X, Y, Zbar, max_order=2, approx=mode != "hard", alpha=alpha,
+                                 function="sigmoid" if mode == "sigmoid" else "hard_sigmoid")
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    out = F.power_bwd(_cfg(mode, max_order=2, reduce_all=True, grid_cols=X.shape[1], grad_mode="nan_parity"), xys, fixed,
+                      grid, Zbar.reshape(-1), alpha=alpha, device="cuda")
+    out = {k: v.cpu().numpy() for k, v in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
+    n_nan = 0
+    for k, ko in (("grid", "grid"), ("fixed", "fixed"), ("objects", "xys"), ("alpha", "alpha")):
+        got, want = out[k].reshape(-1), go[ko].numpy().reshape(-1)
+        assert np.array_equal(np.isnan(got), np.isnan(want)), \
+            f"{k}: NaN pattern differs ({np.isnan(got).sum()} vs {np.isnan(want).sum()} of {want.size})"
+        n_nan += int(np.isnan(want).sum())
+        ok = ~np.isnan(want)
+        # (values: smooth logic on a REGULAR grid of an axis-aligned scene sits on structural min/max ties, whose
+        # sub-gradient split is convention — DESIGN.md "Ties"; compared where the graph is tie-free)
+        regular = case in ("obstacle_regular", "square_regular")
+        if ok.any() and (mode == "hard" or not regular) and (k != "objects" or case == "basic_generic" or mode == "hard"):
+            scale = max(np.abs(want[ok]).max(), 1e-30)
+            assert np.abs(got[ok] - want[ok]).max() <= 1e-4 * scale + 1e-7, k
+    if case == "basic_generic":
+        assert n_nan == 0
+    elif case in ("obstacle_regular", "geojson_norm"):
+        assert n_nan > 0
+
+
 def test_scene_api_matches_reference_los_kats():
     """tests/test_scene.py:487-627 of the reference: LOS maps are X^2+Y^2, grads [2X, 2Y], shapes/dtypes/order."""
     sc = d.Scene(transmitters={"tx0": d.Point(xy=[0.0, 0.0]), "tx1": d.Point(xy=[0.0, 0.0])},
