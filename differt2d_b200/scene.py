@@ -228,6 +228,9 @@ class Scene:
         alpha = kwargs.pop("alpha", DEFAULT_ALPHA)
         tol = float(kwargs.pop("tol", 1e-2))
         patch = float(kwargs.pop("patch", DEFAULT_PATCH))
+        # extension (not a reference keyword): grad / value_and_grad return NaN wherever jax.grad over the reference's
+        # literal graph does (F.TraceConfig.grad_mode); the default is the clean gradient
+        nan_parity = bool(kwargs.pop("nan_parity", False))
         if kwargs:
             raise TypeError(f"unexpected keyword arguments: {sorted(kwargs)}")
         fname, r_coef, height = _resolve_fun(fun, fun_args, fun_kwargs)
@@ -237,7 +240,8 @@ class Scene:
         cfg = F.TraceConfig(grid_role=grid_role, min_order=min_order, max_order=max_order,
                             filter_nodes=self._filter_nodes(filter_objects), method=method, steps=steps, many=many,
                             lr=0.1, mode=mode, tol=tol, patch=patch, fun="received_power" if fname == "generic" else fname,
-                            r_coef=r_coef, height=height, reduce_all=bool(reduce_all))
+                            r_coef=r_coef, height=height, reduce_all=bool(reduce_all),
+                            grad_mode="nan_parity" if nan_parity else "clean")
         self._generic = fname == "generic"
         return cfg, alpha
 

@@ -93,6 +93,13 @@ def test_unsupported_requests_raise():
            (2, 2, 7, 0.3, 0.0, "hard_sigmoid", 0.5) and alpha == 12.0
 
 
+def test_nan_parity_keyword_selects_the_gradient_mode():
+    sc = d.Scene.basic_scene()
+    args = ("receivers", d.received_power, (), None, True, d.ImagePath, None, 0, 1, None, None)
+    assert sc._config(*args, {})[0].grad_mode == "clean"
+    assert sc._config(*args, {"nan_parity": True})[0].grad_mode == "nan_parity"
+
+
 def test_row_blocks_partition_the_grid():
     for n in (1, 7, 10, 1024, 2048):
         for w in (1, 2, 3, 4, 8):
