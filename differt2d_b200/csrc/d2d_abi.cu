@@ -357,24 +357,48 @@ struct DevBuf {
         return 0;
     }
 };
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap && p) return 0;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        const cudaError_t e = cudaMallocHost(&p, n < 256 ? 256 : n);
+        if (e != cudaSuccess) return (int)e;
+        cap = n < 256 ? 256 : n;
+        return 0;
+    }
+};
+constexpr int kHostStreams = 3;
+constexpr int kHostMaxChunks = 8;
 std::mutex g_host_mu;
 DevBuf g_in, g_out;
-cudaStream_t g_host_stream = nullptr;
+PinnedBuf g_partials;
+cudaStream_t g_host_streams[kHostStreams] = {nullptr, nullptr, nullptr};
+cudaEvent_t g_host_ready = nullptr;
 int g_host_stream_dev = -1;
 }  // namespace
 
+// Large 2-D grids are traced in row chunks on three streams: the upload of chunk c + 1 and the download of chunk c - 1
+// overlap the kernels of chunk c (the copies are a quarter of a step otherwise: 12.6 MB each way for 1024^2 points).
+// Every chunk is an independent d2d_power_fwd / d2d_power_bwd pair on whole macro tiles (rows in multiples of 32);
+// the scene-parameter cotangents of the chunks are partial sums, added on the host.
 int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* grid_bar, float* objects_bar,
                    float* phis_bar, float* fixed_bar, float* alpha_bar, int32_t device) {
     if (!hp) return fail(D2D_ERR_INVALID_ARGUMENT, "problem is NULL");
     std::lock_guard<std::mutex> lock(g_host_mu);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    if (!g_host_stream || g_host_stream_dev != device) {
-        if ((e = cudaStreamCreateWithFlags(&g_host_stream, cudaStreamNonBlocking)) != cudaSuccess)
-            return cuda_fail(e, "cudaStreamCreate");
+    if (!g_host_streams[0] || g_host_stream_dev != device) {
+        for (int i = 0; i < kHostStreams; ++i)
+            if ((e = cudaStreamCreateWithFlags(&g_host_streams[i], cudaStreamNonBlocking)) != cudaSuccess)
+                return cuda_fail(e, "cudaStreamCreate");
+        if ((e = cudaEventCreateWithFlags(&g_host_ready, cudaEventDisableTiming)) != cudaSuccess)
+            return cuda_fail(e, "cudaEventCreate");
         g_host_stream_dev = device;
     }
-    cudaStream_t s = g_host_stream;
     const size_t N = (size_t)hp->n_objects, T = (size_t)hp->n_fixed, R = (size_t)hp->n_grid;
     const size_t Tout = hp->reduce_all ? 1 : T;
     D2DProblem dp = *hp;
@@ -382,65 +406,130 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
     if (hp->alpha_dev) dp.alpha = *hp->alpha_dev;  // host scalar in this entry
     const long long C = d2d_problem_num_candidates(&dp);
     if (C < 0) return D2D_ERR_INVALID_ARGUMENT;
+    const bool want_bwd = grid_bar || objects_bar || phis_bar || fixed_bar || alpha_bar;
+    // chunking: rows in multiples of 32 (whole macro tiles), about a quarter of the grid each
+    int n_chunks = 1;
+    size_t chunk_pts = R;
+    const size_t cols = (hp->grid_cols > 0 && R % (size_t)hp->grid_cols == 0) ? (size_t)hp->grid_cols : 0;
+    if (cols > 0 && R >= (size_t)1 << 18) {
+        const size_t rows = R / cols;
+        size_t rows_c = ((rows + 3) / 4 + 31) / 32 * 32;
+        if (rows_c < rows) {
+            chunk_pts = rows_c * cols;
+            n_chunks = (int)((R + chunk_pts - 1) / chunk_pts);
+            if (n_chunks > kHostMaxChunks) { n_chunks = 1; chunk_pts = R; }
+        }
+    }
     auto al = [](size_t n) { return (n + 255) / 256 * 256; };
-    // input arena
+    const size_t x0_bytes = hp->x0 ? (size_t)C * (hp->many > 1 ? hp->many : 1) * hp->max_order * 4 : 0;
+    // input arena: scene | grid (whole) | Zbar (chunk-local [Tout, Rc] blocks, one per chunk)
     const size_t o_xys = 0, o_kind = o_xys + al(N * 16), o_phi = o_kind + al(N), o_fix = o_phi + al(N * 4),
-                 o_grid = o_fix + al(T * 8), o_x0 = o_grid + al(R * 8),
-                 o_zbar = o_x0 + al(hp->x0 ? (size_t)C * (hp->many > 1 ? hp->many : 1) * hp->max_order * 4 : 0),
-                 in_total = o_zbar + al(Zbar ? Tout * R * 4 : 0);
+                 o_x0 = o_fix + al(T * 8), o_grid = o_x0 + al(x0_bytes), o_zbar = o_grid + al(R * 8),
+                 in_total = o_zbar + (Zbar ? (size_t)n_chunks * al(Tout * chunk_pts * 4) : 0);
     int rc = g_in.ensure(in_total, device);
     if (rc) return cuda_fail(rc, "cudaMalloc(inputs)");
     char* din = (char*)g_in.p;
-    auto h2d = [&](size_t off, const void* src, size_t n) {
+    // output arena per chunk: Z | grid_bar | objects_bar | phis_bar | fixed_bar | alpha_bar | mask
+    D2DProblem probe = dp;
+    probe.n_grid = (int64_t)chunk_pts;
+    probe.objects_xys = (const float*)din;  // (non-NULL placeholders: only sizes matter for the mask size)
+    probe.fixed_xy = (const float*)din;
+    probe.grid_xy = (const float*)din;
+    const long long mask_words = want_bwd ? d2d_active_mask_words(&probe) : 0;
+    if (mask_words < 0) return D2D_ERR_INVALID_ARGUMENT;
+    const size_t q_z = 0, q_gb = q_z + al(Tout * chunk_pts * 4), q_ob = q_gb + al(grid_bar ? Tout * chunk_pts * 8 : 0),
+                 q_pb = q_ob + al(N * 16), q_fb = q_pb + al(N * 4), q_ab = q_fb + al(T * 8), q_mask = q_ab + 256,
+                 q_total = q_mask + al((size_t)mask_words * 4) + 256;
+    rc = g_out.ensure(q_total * n_chunks, device);
+    if (rc) return cuda_fail(rc, "cudaMalloc(outputs)");
+    char* dout = (char*)g_out.p;
+    // pinned staging for the per-chunk parameter cotangents
+    const size_t part_floats = 5 * N + 2 * T + 1;
+    if (n_chunks > 1 && want_bwd) {
+        rc = g_partials.ensure((size_t)n_chunks * part_floats * 4);
+        if (rc) return cuda_fail(rc, "cudaMallocHost(partials)");
+    }
+    // scene tables on stream 0; the other streams wait for them
+    cudaStream_t s0 = g_host_streams[0];
+    auto h2d = [&](cudaStream_t s, size_t off, const void* src, size_t n) {
         if (src && n) cudaMemcpyAsync(din + off, src, n, cudaMemcpyHostToDevice, s);
     };
-    h2d(o_xys, hp->objects_xys, N * 16);
-    h2d(o_kind, hp->object_kinds, N);
-    h2d(o_phi, hp->object_phis, N * 4);
-    h2d(o_fix, hp->fixed_xy, T * 8);
-    h2d(o_grid, hp->grid_xy, R * 8);
-    if (hp->x0) h2d(o_x0, hp->x0, (size_t)C * (hp->many > 1 ? hp->many : 1) * hp->max_order * 4);
-    if (Zbar) h2d(o_zbar, Zbar, Tout * R * 4);
+    h2d(s0, o_xys, hp->objects_xys, N * 16);
+    h2d(s0, o_kind, hp->object_kinds, N);
+    h2d(s0, o_phi, hp->object_phis, N * 4);
+    h2d(s0, o_fix, hp->fixed_xy, T * 8);
+    if (hp->x0) h2d(s0, o_x0, hp->x0, x0_bytes);
+    cudaEventRecord(g_host_ready, s0);
     dp.objects_xys = (const float*)(din + o_xys);
     dp.object_kinds = hp->object_kinds ? (const uint8_t*)(din + o_kind) : nullptr;
     dp.object_phis = hp->object_phis ? (const float*)(din + o_phi) : nullptr;
     dp.fixed_xy = (const float*)(din + o_fix);
-    dp.grid_xy = (const float*)(din + o_grid);
     dp.x0 = hp->x0 ? (const float*)(din + o_x0) : nullptr;
-    // output arena
-    const bool want_bwd = grid_bar || objects_bar || phis_bar || fixed_bar || alpha_bar;
-    const long long mask_words = want_bwd ? d2d_active_mask_words(&dp) : 0;
-    if (mask_words < 0) return D2D_ERR_INVALID_ARGUMENT;
-    const size_t q_z = 0, q_gb = q_z + al(Tout * R * 4), q_ob = q_gb + al(grid_bar ? Tout * R * 8 : 0),
-                 q_pb = q_ob + al(N * 16), q_fb = q_pb + al(N * 4), q_ab = q_fb + al(T * 8), q_mask = q_ab + 256,
-                 out_total = q_mask + al((size_t)mask_words * 4) + 256;
-    rc = g_out.ensure(out_total, device);
-    if (rc) return cuda_fail(rc, "cudaMalloc(outputs)");
-    char* dout = (char*)g_out.p;
-    if (want_bwd) {
-        // value, then the VJP over the paths the forward found alive (the activity mask is the only residual)
-        dp.active_mask = (uint32_t*)(dout + q_mask);
-        rc = d2d_power_fwd(&dp, (float*)(dout + q_z), nullptr, s);
-        if (rc != D2D_OK) return rc;
-        rc = d2d_power_bwd(&dp, Zbar ? (const float*)(din + o_zbar) : nullptr, nullptr,
-                           grid_bar ? (float*)(dout + q_gb) : nullptr, objects_bar ? (float*)(dout + q_ob) : nullptr,
-                           phis_bar ? (float*)(dout + q_pb) : nullptr, fixed_bar ? (float*)(dout + q_fb) : nullptr,
-                           alpha_bar ? (float*)(dout + q_ab) : nullptr, s);
-    } else {
-        rc = d2d_power_fwd(&dp, (float*)(dout + q_z), nullptr, s);
+    for (int c = 0; c < n_chunks; ++c) {
+        cudaStream_t s = g_host_streams[c % kHostStreams];
+        if (s != s0 || c >= kHostStreams) cudaStreamWaitEvent(s, g_host_ready, 0);
+        const size_t r0 = (size_t)c * chunk_pts, Rc = (r0 + chunk_pts <= R) ? chunk_pts : R - r0;
+        char* qo = dout + (size_t)c * q_total;
+        const size_t zb_off = o_zbar + (size_t)c * al(Tout * chunk_pts * 4);
+        h2d(s, o_grid + r0 * 8, hp->grid_xy ? (const char*)hp->grid_xy + r0 * 8 : nullptr, Rc * 8);
+        if (Zbar)
+            for (size_t t = 0; t < Tout; ++t) h2d(s, zb_off + t * Rc * 4, Zbar + t * R + r0, Rc * 4);
+        D2DProblem cp = dp;
+        cp.n_grid = (int64_t)Rc;
+        cp.grid_xy = (const float*)(din + o_grid + r0 * 8);
+        if (want_bwd) {
+            // value, then the VJP over the paths the forward found alive (the activity mask is the only residual)
+            cp.active_mask = (uint32_t*)(qo + q_mask);
+            rc = d2d_power_fwd(&cp, (float*)(qo + q_z), nullptr, s);
+            if (rc != D2D_OK) break;
+            rc = d2d_power_bwd(&cp, Zbar ? (const float*)(din + zb_off) : nullptr, nullptr,
+                               grid_bar ? (float*)(qo + q_gb) : nullptr, objects_bar ? (float*)(qo + q_ob) : nullptr,
+                               phis_bar ? (float*)(qo + q_pb) : nullptr, fixed_bar ? (float*)(qo + q_fb) : nullptr,
+                               alpha_bar ? (float*)(qo + q_ab) : nullptr, s);
+        } else {
+            cp.active_mask = nullptr;
+            rc = d2d_power_fwd(&cp, (float*)(qo + q_z), nullptr, s);
+        }
+        if (rc != D2D_OK) break;
+        auto d2h = [&](void* dst, size_t off, size_t n) {
+            if (dst && n) cudaMemcpyAsync(dst, qo + off, n, cudaMemcpyDeviceToHost, s);
+        };
+        for (size_t t = 0; t < Tout; ++t) {
+            if (Z) d2h(Z + t * R + r0, q_z + t * Rc * 4, Rc * 4);
+            if (grid_bar) d2h(grid_bar + 2 * (t * R + r0), q_gb + t * Rc * 8, Rc * 8);
+        }
+        if (n_chunks == 1) {
+            d2h(objects_bar, q_ob, N * 16);
+            d2h(phis_bar, q_pb, N * 4);
+            d2h(fixed_bar, q_fb, T * 8);
+            d2h(alpha_bar, q_ab, 4);
+        } else if (want_bwd) {
+            float* part = (float*)g_partials.p + (size_t)c * part_floats;
+            if (objects_bar) d2h(part, q_ob, N * 16);
+            if (phis_bar) d2h(part + 4 * N, q_pb, N * 4);
+            if (fixed_bar) d2h(part + 5 * N, q_fb, T * 8);
+            if (alpha_bar) d2h(part + 5 * N + 2 * T, q_ab, 4);
+        }
+    }
+    for (int i = 0; i < kHostStreams; ++i) {
+        e = cudaStreamSynchronize(g_host_streams[i]);
+        if (e != cudaSuccess && rc == D2D_OK) rc = cuda_fail(e, "d2d_power_host");
     }
     if (rc != D2D_OK) return rc;
-    auto d2h = [&](void* dst, size_t off, size_t n) {
-        if (dst && n) cudaMemcpyAsync(dst, dout + off, n, cudaMemcpyDeviceToHost, s);
-    };
-    d2h(Z, q_z, Tout * R * 4);
-    d2h(grid_bar, q_gb, Tout * R * 8);
-    d2h(objects_bar, q_ob, N * 16);
-    d2h(phis_bar, q_pb, N * 4);
-    d2h(fixed_bar, q_fb, T * 8);
-    d2h(alpha_bar, q_ab, 4);
-    e = cudaStreamSynchronize(s);
-    if (e != cudaSuccess) return cuda_fail(e, "d2d_power_host");
+    if (n_chunks > 1 && want_bwd) {  // partial sums of the chunks, in chunk order
+        auto add = [&](float* dst, size_t off, size_t n) {
+            if (!dst) return;
+            for (size_t i = 0; i < n; ++i) {
+                float acc = 0.0f;
+                for (int c = 0; c < n_chunks; ++c) acc += ((const float*)g_partials.p)[(size_t)c * part_floats + off + i];
+                dst[i] = acc;
+            }
+        };
+        add(objects_bar, 0, 4 * N);
+        add(phis_bar, 4 * N, N);
+        add(fixed_bar, 5 * N, 2 * T);
+        add(alpha_bar, 5 * N + 2 * T, 1);
+    }
     return D2D_OK;
 }
 

@@ -211,6 +211,52 @@ def power_bwd(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis
     return out
 
 
+def power_host(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA, x0=None,
+               want=("Z", "grid", "objects", "phis", "fixed", "alpha"), device: int = 0) -> dict:
+    """
+    The host-buffer entry (d2d_power_host): numpy arrays in, numpy arrays out, the library stages them (large 2-D
+    grids in row chunks on three streams, copies overlapping the kernels), runs the forward kernel and — when a
+    cotangent is wanted — the backward kernel over the activity mask, and synchronises.  What a numpy user of the
+    reference calls; `bench.py`'s end-to-end leg.
+    """
+    if not torch.cuda.is_available():
+        raise L.D2DError("differt2d_b200 computes on CUDA devices only (no CPU fallback)")
+    f32 = lambda a: np.ascontiguousarray(np.asarray(a, dtype=np.float32))  # noqa: E731
+    xys_h, fixed_h, grid_h = f32(xys).reshape(-1, 2, 2), f32(fixed).reshape(-1, 2), f32(grid).reshape(-1, 2)
+    N, T, R = xys_h.shape[0], fixed_h.shape[0], grid_h.shape[0]
+    Tout = 1 if cfg.reduce_all else T
+    kinds_h = None if kinds is None else np.ascontiguousarray(np.asarray(kinds, dtype=np.uint8))
+    phis_h = None if phis is None else f32(phis).reshape(N)
+    x0_h = None if x0 is None else f32(x0)
+    zbar_h = None if Zbar is None else f32(Zbar).reshape(Tout, R)
+    flt = np.ascontiguousarray(np.asarray(cfg.filter_nodes, dtype=np.int32))
+    p = L.new_problem()
+    p.n_objects, p.objects_xys = N, xys_h.ctypes.data
+    p.object_kinds = kinds_h.ctypes.data if kinds_h is not None else None
+    p.object_phis = phis_h.ctypes.data if phis_h is not None else None
+    p.n_fixed, p.fixed_xy = T, fixed_h.ctypes.data
+    p.n_grid, p.grid_xy = R, grid_h.ctypes.data
+    p.grid_role = ROLES[cfg.grid_role]
+    p.min_order, p.max_order = int(cfg.min_order), int(cfg.max_order)
+    p.filter_nodes, p.n_filter = (flt.ctypes.data if flt.size else None), int(flt.size)
+    p.method, p.steps, p.many, p.lr = METHODS[cfg.method], int(cfg.steps), int(cfg.many), float(cfg.lr)
+    p.x0 = x0_h.ctypes.data if x0_h is not None else None
+    p.mode, p.alpha, p.tol, p.patch = MODES[cfg.mode], float(alpha), float(cfg.tol), float(cfg.patch)
+    p.fun, p.r_coef, p.height = FUNS[cfg.fun], float(cfg.r_coef), float(cfg.height)
+    p.reduce_all, p.grid_cols = int(cfg.reduce_all), int(cfg.grid_cols)
+    p.no_cull, p.candidate_slices = (0 if cfg.cull else 1), int(cfg.candidate_slices)
+    p.grad_mode = GRAD_MODES[cfg.grad_mode]
+    shapes = {"Z": (Tout, R) if not cfg.reduce_all else (R,), "grid": ((Tout, R, 2) if not cfg.reduce_all else (R, 2)),
+              "objects": (N, 2, 2), "phis": (N,), "fixed": (T, 2), "alpha": (1,)}
+    out = {k: np.empty(shapes[k], dtype=np.float32) for k in want}
+    ptr = lambda k: out[k].ctypes.data if k in out else None  # noqa: E731
+    zsink = out["Z"] if "Z" in out else np.empty(shapes["Z"], dtype=np.float32)
+    rc = L.lib().d2d_power_host(C.byref(p), zbar_h.ctypes.data if zbar_h is not None else None, zsink.ctypes.data,
+                                ptr("grid"), ptr("objects"), ptr("phis"), ptr("fixed"), ptr("alpha"), int(device))
+    L.check(rc, "d2d_power_host")
+    return out
+
+
 _REC_WORDS = C.sizeof(L.D2DPathRecord) // 4  # the record as 32-bit words
 
 

@@ -207,6 +207,29 @@ def test_nan_parity_gradient_mode(case, mode, alpha):
         assert n_nan > 0
 
 
+@pytest.mark.parametrize("n,m,reduce_all", [(24, 40, True), (24, 40, False), (512, 512, True), (544, 512, False)])
+def test_host_entry_equals_device_entry(n, m, reduce_all):
+    """d2d_power_host (numpy in / numpy out; grids of >= 2^18 points go through in row chunks on three streams, the
+    last chunk shorter) against d2d_power_fwd + d2d_power_bwd on device buffers: maps and per-point cotangents bit for
+    bit, scene-parameter cotangents up to the order of the partial sums."""
+    sc = d.Scene.basic_scene().update_transmitters(tx2=d.Point(xy=[0.7, 0.6]))
+    X, Y = sc.grid(m, n)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    Tout = 1 if reduce_all else fixed.shape[0]
+    Zbar = np.random.default_rng(5).standard_normal((Tout, grid.shape[0])).astype(np.float32)
+    cfg = _cfg("hard_sigmoid", max_order=2, reduce_all=reduce_all, grid_cols=m)
+    host = F.power_host(cfg, xys, fixed, grid, Zbar, alpha=30.0)
+    dev = F.power_value_and_vjp(cfg, xys, fixed, grid, Zbar.reshape(-1) if reduce_all else Zbar, alpha=30.0, device="cuda")
+    dev = {k: v.cpu().numpy() for k, v in dev.items()}
+    assert np.array_equal(host["Z"].reshape(-1), dev["Z"].reshape(-1))
+    assert np.array_equal(host["grid"].reshape(-1), dev["grid"].reshape(-1))
+    for k in ("objects", "fixed", "alpha"):
+        _close(host[k].reshape(-1), dev[k].reshape(-1), 2e-4, k)  # fp32 atomics: the order of the partial sums differs
+    assert np.abs(dev["objects"]).max() > 0 and np.abs(dev["Z"]).max() > 0
+
+
 def test_scene_api_matches_reference_los_kats():
     """tests/test_scene.py:487-627 of the reference: LOS maps are X^2+Y^2, grads [2X, 2Y], shapes/dtypes/order."""
     sc = d.Scene(transmitters={"tx0": d.Point(xy=[0.0, 0.0]), "tx1": d.Point(xy=[0.0, 0.0])},
