@@ -116,7 +116,7 @@ class ClockSampler:
                     self.power.append(N.nvmlDeviceGetPowerUsage(self.h) / 1e3)
                 except Exception:
                     pass
-            time.sleep(0.0005)
+            time.sleep(0.002)
 
     def mark_start(self):
         self.live = True

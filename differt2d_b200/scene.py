@@ -140,6 +140,53 @@ class Scene:
                 rx=Point(xy=Scene(objects=walls).get_location(rx_loc)))
         return sc.with_transmitters(tx=Point(xy=[0.0, 0.0])).with_receivers(rx=Point(xy=[1.0, 1.0]))
 
+    def sanitised(self, drop_zero_length: bool = True, normalise: bool = False, return_map: bool = False):
+        """
+        SURVEY §8 (f)2 — a scene the fp32 path tracer is well conditioned on (NOT part of the reference: results
+        differ from the raw scene's, which stays the parity case).
+
+        * ``drop_zero_length``: removes zero-length walls — `from_geojson` emits one closure wall per polygon ring
+          (scene.py:646-652: ``coords[i - 1]`` wraps to the duplicated last vertex).  Every candidate through such a
+          wall is invalid (n = 0, loss = 1) but poisons the reference's reverse mode with NaN (geometry.py:1105).
+        * ``normalise``: shifts / scales all coordinates to the unit square (computed in float64).  Raw lon/lat
+          coordinates (|y| ~ 50) put ~3 % of a wall length of fp32 lattice noise on every parametric coordinate;
+          distances change by the scale factor, so `received_power`'s `height` has to be rescaled by the caller
+          (the factor is returned with the map).
+
+        ``return_map``: also returns ``{"kept": indices of the kept objects, "origin": [2], "scale": float}`` so that
+        cotangents w.r.t. the sanitised vertices can be carried back (d/d raw = d/d sanitised / scale).
+        """
+        kept = [i for i, o in enumerate(self.objects)
+                if not (drop_zero_length and isinstance(o, Wall) and not np.any(o.xys[1] != o.xys[0]))]
+        objs = [self.objects[i] for i in kept]
+        origin, scale = np.zeros(2, np.float64), 1.0
+        tx, rx = self.transmitters, self.receivers
+        if normalise:
+            bb = Scene(tx, rx, objs).bounding_box().astype(np.float64)
+            origin = bb[0]
+            scale = float(max(bb[1, 0] - bb[0, 0], bb[1, 1] - bb[0, 1])) or 1.0
+
+            def f(a):
+                return ((np.asarray(a, np.float64) - origin) / scale).astype(np.float32)
+
+            moved = []
+            for o in objs:
+                if isinstance(o, Vertex):
+                    moved.append(Vertex(xy=f(o.xy)))
+                elif isinstance(o, RIS):
+                    moved.append(RIS(xys=f(o.xys), phi=o.phi))
+                elif isinstance(o, Wall):
+                    moved.append(Wall(xys=f(o.xys)))
+                else:
+                    raise NotImplementedError(f"object type {type(o).__name__}")
+            objs = moved
+            tx = {k: Point(xy=f(p.xy)) for k, p in tx.items()}
+            rx = {k: Point(xy=f(p.xy)) for k, p in rx.items()}
+        sc = Scene(tx, rx, objs)
+        if return_map:
+            return sc, {"kept": kept, "origin": origin.astype(np.float64), "scale": scale}
+        return sc
+
     # ---- Plottable pieces needed to build inputs (abc.py:30-126, scene.py:1023-1036) --------------
     def bounding_box(self) -> np.ndarray:
         boxes = [p.bounding_box() for p in self.transmitters.values()]

@@ -100,6 +100,23 @@ def test_nan_parity_keyword_selects_the_gradient_mode():
     assert sc._config(*args, {"nan_parity": True})[0].grad_mode == "nan_parity"
 
 
+def test_sanitised_scene_drops_closure_walls_and_normalises():
+    from tests import helpers as H
+
+    sc = d.Scene.from_geojson(H.geojson_text())
+    assert len(sc.objects) == 28                                   # tests/test_scene.py:217-238 of the reference
+    clean, info = sc.sanitised(return_map=True)
+    assert len(clean.objects) == 26 and sorted(set(range(28)) - set(info["kept"])) == [0, 7]
+    assert all(np.any(o.xys[0] != o.xys[1]) for o in clean.objects)
+    assert np.array_equal(clean.objects[0].xys, sc.objects[1].xys) and info["scale"] == 1.0
+    unit, info = sc.sanitised(normalise=True, return_map=True)
+    bb = unit.bounding_box()
+    assert np.allclose(bb[0], 0.0, atol=1e-6) and abs(bb[1].max() - 1.0) < 1e-6 and bb[1].min() > 0.0
+    back = np.asarray(unit.objects[3].xys, np.float64) * info["scale"] + info["origin"]
+    assert np.allclose(back, np.asarray(sc.objects[info["kept"][3]].xys, np.float64), atol=1e-9 + 1e-6 * info["scale"])
+    assert set(unit.transmitters) == set(sc.transmitters) and set(unit.receivers) == set(sc.receivers)
+
+
 def test_row_blocks_partition_the_grid():
     for n in (1, 7, 10, 1024, 2048):
         for w in (1, 2, 3, 4, 8):
