@@ -335,11 +335,11 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
                     float onx;
                     const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
                     if (image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx))
-                        valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
+                        valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx, &sh.hint[threadIdx.x >> 5]);
                 } else {
                     float loss;
                     construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-                    valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+                    valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss, &sh.hint[threadIdx.x >> 5]);
                 }
                 if (valid != 0.0f) {
                     const float c = path_vjp<MODE, METHOD, K>(T, p, alpha, cd, tx, rx, col, zbar, has, txb, rxb, ab,

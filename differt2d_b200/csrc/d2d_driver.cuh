@@ -75,6 +75,7 @@ struct Tile {
 
 struct DriverShared {
     int count;               // n_allowed
+    int hint[kBlock / 32];   // per warp: the object that blocked its previous path (intersects_x starts its fold there)
     float red[4][4];         // per-warp partials
     int wcount[2][4];        // survivors per warp segment, double buffered
     int4 list[2][kBlock];    // packed survivors: (c0 | c1 << 16, c2 | c3 << 16, index lo, index hi)
@@ -166,6 +167,7 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     const int warp = tid >> 5, lane = tid & 31;
     if (lane == 0) {
         sh.red[warp][0] = xmin; sh.red[warp][1] = ymin; sh.red[warp][2] = xmax; sh.red[warp][3] = ymax;
+        sh.hint[warp] = 0;
     }
     __syncthreads();
     xmin = fminf(fminf(sh.red[0][0], sh.red[1][0]), fminf(sh.red[2][0], sh.red[3][0]));

@@ -33,12 +33,12 @@ __device__ __forceinline__ void run_order(const SceneTab& T, const KParams& p, c
                         bool dg = false;
                         for (int i = 0; i < K; ++i) dg = dg || (T.w0[cd.c[i]].z == 0.f && T.w0[cd.c[i]].w == 0.f);
                         if (dg) D2D_COUNT(18);
-                        valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
+                        valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx, &sh.hint[threadIdx.x >> 5]);
                     }
                 } else {
                     float loss;
                     construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-                    valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss);
+                    valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss, &sh.hint[threadIdx.x >> 5]);
                 }
                 if (valid != 0.0f) {
                     D2D_COUNT(19);

@@ -32,16 +32,16 @@ __device__ __forceinline__ void run_order_paths(const SceneTab& T, const KParams
             if (out.emit_all) {
                 construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
                 if (!kSolverLoss) loss = path_loss<K>(T, cd, X);  // geometry.py:1077-1084, 1202-1204
-                valid = validity<MODE, K, false>(T, p, alpha, cd, X, loss);
+                valid = validity<MODE, K, false>(T, p, alpha, cd, X, loss, &sh.hint[threadIdx.x >> 5]);
             } else {
                 if constexpr (METHOD == D2D_METHOD_IMAGE) {
                     float onx;
                     const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
                     if (!image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx)) return;
-                    valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx);
+                    valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx, &sh.hint[threadIdx.x >> 5]);
                 } else {
                     construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-                    valid = validity<MODE, K, !kSolverLoss>(T, p, alpha, cd, X, loss);
+                    valid = validity<MODE, K, !kSolverLoss>(T, p, alpha, cd, X, loss, &sh.hint[threadIdx.x >> 5]);
                 }
                 if (!(valid > out.min_valid)) return;
                 if (!kSolverLoss) loss = path_loss<K>(T, cd, X);

@@ -132,10 +132,14 @@ __device__ __forceinline__ float path_loss(const SceneTab& T, const Cand<K>& cd,
 // first arg-max in the reference's (segment, object) order.
 // Fast path per test: canonical a, b, d; approximate parameters through one MUFU.RCP and two FMAs; the exact
 // IEEE divisions (hit_exact, out of line) only run when the test could raise the running maximum `interx`.
+// `hint` (forward-style calls only, TRACK = false): a per-warp slot holding the object that blocked the warp's previous
+// path.  The fold then starts there and wraps around: neighbouring candidates and receivers are mostly blocked by the
+// same wall, and a blocked path leaves the loop at its blocker (95 % of the paths that reach the fold are blocked; in
+// list order they scan half the scene first).  max is exact and commutative, so the value does not depend on the order.
 template <int MODE, int K, bool TRACK>
 __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, const Cand<K>& cd,
                                               const float2 (&X)[K + 2], const float alpha, bool& alive,
-                                              int& arg_seg, int& arg_j) {
+                                              int& arg_seg, int& arg_j, int* hint = nullptr) {
     float interx = -CUDART_INF_F;
     const float xz = x_zero<MODE>(alpha);
     float cthr = filter_threshold(xz);
@@ -147,8 +151,15 @@ __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, co
         sa[i] = (i > 0) ? cd.c[i > 0 ? i - 1 : 0] : -1;  // the segment's own end objects are skipped
         sb[i] = (i < K) ? cd.c[i < K ? i : 0] : -1;
     }
+    int j0 = 0, blocker = -1;
+    if (!TRACK && hint) {
+        j0 = *reinterpret_cast<volatile int*>(hint);
+        if (j0 >= N) j0 = 0;
+    }
 #pragma unroll 1
-    for (int j = 0; j < N; ++j) {
+    for (int jj = 0; jj < N; ++jj) {
+        int j = jj + j0;
+        if (j >= N) j -= N;
         const float4 w = T.w2[j];
 #pragma unroll
         for (int i = 0; i <= K; ++i) {
@@ -173,8 +184,12 @@ __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, co
                 }
             }
         }
-        if (!alive) break;
+        if (!alive) {
+            blocker = j;
+            break;
+        }
     }
+    if (!TRACK && hint && blocker >= 0) *reinterpret_cast<volatile int*>(hint) = blocker;  // (any lane's: a heuristic)
     return interx;
 }
 
@@ -193,18 +208,18 @@ __device__ __forceinline__ float path_value(const KParams& p, const float2 (&X)[
 template <int MODE, int K, bool LAZY_LOSS>
 __device__ __forceinline__ float validity_from_onx(const SceneTab& T, const KParams& p, const float alpha,
                                                    const Cand<K>& cd, const float2 (&X)[K + 2], float loss,
-                                                   const float onx);
+                                                   const float onx, int* hint = nullptr);
 
 template <int MODE, int K, bool LAZY_LOSS>
 __device__ __forceinline__ float validity(const SceneTab& T, const KParams& p, const float alpha,
-                                          const Cand<K>& cd, const float2 (&X)[K + 2], float loss) {
-    return validity_from_onx<MODE, K, LAZY_LOSS>(T, p, alpha, cd, X, loss, on_objects_x<K>(T, cd, X));
+                                          const Cand<K>& cd, const float2 (&X)[K + 2], float loss, int* hint = nullptr) {
+    return validity_from_onx<MODE, K, LAZY_LOSS>(T, p, alpha, cd, X, loss, on_objects_x<K>(T, cd, X), hint);
 }
 
 template <int MODE, int K, bool LAZY_LOSS>
 __device__ __forceinline__ float validity_from_onx(const SceneTab& T, const KParams& p, const float alpha,
                                                    const Cand<K>& cd, const float2 (&X)[K + 2], float loss,
-                                                   const float onx) {
+                                                   const float onx, int* hint) {
     // 1. on_objects
     float a_on = 1.0f;
     if (MODE == D2D_MODE_HARD) {
@@ -227,7 +242,7 @@ __device__ __forceinline__ float validity_from_onx(const SceneTab& T, const KPar
     // 3. occlusion
     bool alive = true;
     int seg = 0, jj = 0;
-    const float interx = intersects_x<MODE, K, false>(T, p.N, cd, X, alpha, alive, seg, jj);
+    const float interx = intersects_x<MODE, K, false>(T, p.N, cd, X, alpha, alive, seg, jj, hint);
     if (!alive) return 0.0f;
     if (MODE == D2D_MODE_HARD) return 1.0f;
     const float a_in = (interx == -CUDART_INF_F) ? 0.0f : act<MODE>(interx, alpha);
