@@ -464,6 +464,9 @@ def main() -> None:
         traffic = ncu[dom]["dram_bytes_read"] + ncu[dom]["dram_bytes_write"]
         executed = {k: ncu[dom][k] for k in ("issue_slots_busy_pct", "fp32_lanes_busy_pct", "executed_fp32_flop",
                                              "warp_instructions", "achieved_occupancy_pct")}
+        ex_tf = ncu[dom]["executed_fp32_flop"] / (ncu[dom]["duration_ms_under_ncu"] * 1e-3) / 1e12
+        executed["fp32_tflops"] = ex_tf
+        executed["fp32_frac_of_peak"] = ex_tf / peak_tf if peak_tf else None
         executed["source"] = "profiles/ncu_metrics.json (ncu --set full of this command, per launch)"
     algo_bytes = R * (8 + 4 + 4 + 8)  # grid in, Zbar in, Z out... per launch of the dominant kernel
     line = {

@@ -404,8 +404,7 @@ __device__ __forceinline__ bool warp_may_be_valid(const float4 w0, const float4 
     return !(smax < xz - tol || smin > 1.0f - xz + tol);
 }
 
-// One candidate, out of line (ONE copy of the decode + image chain + tile test per order in a translation unit: the
-// macro stage and the tile stage both call it, and these kernels are instruction-fetch bound).
+// One candidate: decode + image chain + tile test.
 struct CandTest {
     int c01, c23;     // objects, 16 bits each
     float2 apex;      // image of the fixed point through all objects (ImagePath on a receivers grid)
@@ -414,26 +413,37 @@ struct CandTest {
 };
 
 template <int K>
-__device__ __noinline__ CandTest test_candidate(unsigned char* smem, const int N, const int m, const long long idx,
-                                                const float2 fx, const bool apex_wanted, const bool cull,
-                                                const float4 box, const float scale, const float scale_x,
-                                                const float scale_y, const float xz, const float loss_dead) {
+__device__ __forceinline__ CandTest test_candidate_inline(const SceneTab& T, const int m, const long long idx,
+                                                          const float2 fx, const bool apex_wanted, const bool cull,
+                                                          const float4 box, const float scale, const float scale_x,
+                                                          const float scale_y, const float xz, const float loss_dead) {
     constexpr int KK = K > 0 ? K : 1;
-    const SceneTab T = carve_tab(smem, N);
     CandTest o;
     o.apex = fx;
     o.tol_last = CUDART_INF_F;
     o.keep = true;
     // index -> positions in `allowed` (lexicographic, no equal neighbours)
     int c[KK];
-    long long rem = idx;
     int dig[KK];
+    if ((idx >> 32) == 0) {  // (uniform in practice) 32-bit quotients: a 64-bit division is ~5x the instructions
+        unsigned rem = (unsigned)idx;
+        const unsigned dv = (unsigned)(m - 1);
 #pragma unroll
-    for (int i = K - 1; i >= 1; --i) {
-        dig[i] = (int)(rem % (m - 1));
-        rem /= (m - 1);
+        for (int i = K - 1; i >= 1; --i) {
+            const unsigned q = rem / dv;
+            dig[i] = (int)(rem - q * dv);
+            rem = q;
+        }
+        dig[0] = (int)rem;
+    } else {
+        long long rem = idx;
+#pragma unroll
+        for (int i = K - 1; i >= 1; --i) {
+            dig[i] = (int)(rem % (m - 1));
+            rem /= (m - 1);
+        }
+        dig[0] = (int)rem;
     }
-    dig[0] = (int)rem;
     int prev = -1;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
@@ -456,6 +466,17 @@ __device__ __noinline__ CandTest test_candidate(unsigned char* smem, const int N
         }
     }
     return o;
+}
+
+// The out-of-line copy serves the macro stage (a prologue that runs once per kernel): the chunk loop keeps its own
+// inlined copy, so the hot loop's instruction footprint is what it was before the macro stage existed.
+template <int K>
+__device__ __noinline__ CandTest test_candidate(unsigned char* smem, const int N, const int m, const long long idx,
+                                                const float2 fx, const bool apex_wanted, const bool cull,
+                                                const float4 box, const float scale, const float scale_x,
+                                                const float scale_y, const float xz, const float loss_dead) {
+    const SceneTab T = carve_tab(smem, N);
+    return test_candidate_inline<K>(T, m, idx, fx, apex_wanted, cull, box, scale, scale_x, scale_y, xz, loss_dead);
 }
 
 // number of candidates of order K over m visitable objects
@@ -583,7 +604,6 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     const float xz = x_zero<MODE>(alpha);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-    unsigned char* const smem_tab = reinterpret_cast<unsigned char*>(T.w0);  // (the table starts with w0: carve_tab)
     // a survivor bitmap (macro cull, or the activity mask in the backward kernel) replaces the walk over all columns
     const bool use_macro = (cull && p.macro) || (mread && mask_bitmap_fits(p));  // uniform over the CTA
 
@@ -601,8 +621,8 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
             pre = (any4 >> ((col0 + idx) & 31)) & 1u;
         }
         if (pre)
-            ct = test_candidate<K>(smem_tab, p.N, m, idx, fx, kApex, cull, tile.bbox, tile.scale, tile.scale_x,
-                                   tile.scale_y, xz, p.tol - xz);
+            ct = test_candidate_inline<K>(T, m, idx, fx, kApex, cull, tile.bbox, tile.scale, tile.scale_x, tile.scale_y,
+                                          xz, p.tol - xz);
         const bool keep = ct.keep;
         // ordered compaction: per-warp segments keep list order
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);

@@ -207,7 +207,7 @@ def test_nan_parity_gradient_mode(case, mode, alpha):
         assert n_nan > 0
 
 
-@pytest.mark.parametrize("n,m,reduce_all", [(24, 40, True), (24, 40, False), (512, 512, True), (544, 512, False)])
+@pytest.mark.parametrize("n,m,reduce_all", [(24, 40, True), (24, 40, False), (512, 512, True), (560, 512, False)])
 def test_host_entry_equals_device_entry(n, m, reduce_all):
     """d2d_power_host (numpy in / numpy out; grids of >= 2^18 points go through in row chunks on three streams, the
     last chunk shorter) against d2d_power_fwd + d2d_power_bwd on device buffers: maps and per-point cotangents bit for
