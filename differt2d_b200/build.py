@@ -74,7 +74,8 @@ def _build(verbose: bool, defs, prefix: str, lib_path: str) -> str:
     def compile_one(item):
         src, objname, extra = item
         obj = os.path.join(OUT_DIR, prefix + objname)
-        cmd = [nvcc, *ARCH, *COMMON, *extra, *defs, "-c", os.path.join(CSRC, src), "-o", obj]
+        tune = os.environ.get("D2D_NVCC_EXTRA", "").split()  # tuning experiments, e.g. -DD2D_BWD_MIN_CTAS=4
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *defs, *tune, "-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             cmd.insert(1, "-Xptxas=-v")
             print(" ".join(cmd), flush=True)
