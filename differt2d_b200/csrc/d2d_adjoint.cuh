@@ -69,6 +69,64 @@ __device__ __forceinline__ void residual_adj(const int kind, const float2 a, con
     b_bar.x -= rv_bar.x; b_bar.y -= rv_bar.y;
 }
 
+// normalize_adj with the length normalize2 already produced (same values: len = sqrtf(v.v), 1 when v == 0)
+__device__ __forceinline__ float2 normalize_adj_len(const float2 v, const float len, const bool zero, const float2 vh_bar) {
+    if (zero) return vh_bar;  // v / 1
+    const float inv = 1.0f / len;
+    const float2 vh = make_float2(v.x * inv, v.y * inv);
+    const float pr = dot2(vh_bar, vh);
+    return make_float2((vh_bar.x - pr * vh.x) * inv, (vh_bar.y - pr * vh.y) * inv);
+}
+
+// residual() and residual_adj(..., g = 1) in one pass: the value and the cotangents of the three points, with every
+// segment normalised ONCE (the two separate calls each normalise both segments, and normalize_adj takes the square
+// roots a third time: 6 IEEE square roots and 10 divisions per wall interaction instead of 2 and 6).  Same operations
+// on the same operands in the same order as the separate calls, hence the same bits — this is the inner loop of the
+// MinPath solver (d2d_solver.cuh), whose iterates must not move.
+__device__ __forceinline__ float residual_value_and_grad(const int kind, const float2 a, const float2 b, const float2 c,
+                                                         const float4 w1, const float2 sc, float2& a_bar, float2& b_bar,
+                                                         float2& c_bar) {
+    if (kind == D2D_KIND_VERTEX) return 0.0f;
+    const float2 n = make_float2(w1.x, w1.y);
+    const float2 rv = make_float2(c.x - b.x, c.y - b.y);
+    float lr;
+    const float2 r = normalize2(rv, lr);
+    const bool rzero = rv.x * rv.x + rv.y * rv.y == 0.0f;
+    float2 r_bar;
+    float value;
+    if (kind == D2D_KIND_WALL) {
+        const float2 iv = make_float2(b.x - a.x, b.y - a.y);
+        float li;
+        const float2 i = normalize2(iv, li);
+        const bool izero = iv.x * iv.x + iv.y * iv.y == 0.0f;
+        const float c2 = 2.0f * dot2(i, n);
+        const float2 e = make_float2(r.x - (i.x - c2 * n.x), r.y - (i.y - c2 * n.y));
+        value = e.x * e.x + e.y * e.y;
+        const float2 e_bar = make_float2(2.0f * e.x, 2.0f * e.y);
+        const float en = dot2(e_bar, n);
+        r_bar = e_bar;
+        const float2 i_bar = make_float2(-e_bar.x + 2.0f * en * n.x, -e_bar.y + 2.0f * en * n.y);
+        const float2 iv_bar = normalize_adj_len(iv, li, izero, i_bar);
+        b_bar.x += iv_bar.x; b_bar.y += iv_bar.y;
+        a_bar.x -= iv_bar.x; a_bar.y -= iv_bar.y;
+    } else {  // RIS
+        const float mx = -r.x, my = -r.y;
+        const float sin_a = mx * n.y - my * n.x;
+        const float cos_a = mx * n.x + my * n.y;
+        const float dsv = sin_a - sc.x, dcv = cos_a - sc.y;
+        value = dsv * dsv + dcv * dcv;
+        const float ds = 2.0f * dsv;
+        const float dc = 2.0f * dcv;
+        const float mbx = ds * n.y + dc * n.x;
+        const float mby = -ds * n.x + dc * n.y;
+        r_bar = make_float2(-mbx, -mby);
+    }
+    const float2 rv_bar = normalize_adj_len(rv, lr, rzero, r_bar);
+    c_bar.x += rv_bar.x; c_bar.y += rv_bar.y;
+    b_bar.x -= rv_bar.x; b_bar.y -= rv_bar.y;
+    return value;
+}
+
 // Adjoints of the per-object table entries of one interacting object.
 struct ObjAdj {
     float2 p1;   // origin

@@ -48,10 +48,8 @@ __device__ __forceinline__ float solver_loss_grad(const SceneTab& T, const Cand<
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         const int j = cd.c[i];
-        loss = loss + residual(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j]);
-        float2 nb = make_float2(0.f, 0.f);
-        float pb = 0.f;
-        residual_adj(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j], 1.0f, G[i], G[i + 1], G[i + 2], nb, pb);
+        loss = loss + residual_value_and_grad(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j], G[i], G[i + 1],
+                                              G[i + 2]);
     }
     return loss;
 }
