@@ -233,8 +233,9 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
 //     dX_c <= eps [S + |g||u| + 4|g||u_c| + 4.4 (|u_c|/|un|)(|v|_1 + |g||u|_1)] + L dev
 //     ds   <= (|t_x| dX_x + |t_y| dX_y)/tt + 4 eps |s|
 // with L = (1 + |g|)(1 + |u|/|un|) the Lipschitz constant of p -> X and dev the distance of the thread's
-// computed p from the convex set used here.  tol = 2.5 ds + 1e-6 covers both the threads' evaluation and the
-// (FMA-contracted) evaluation at the extreme points.
+// computed p from the convex set used here.  The evaluation at the extreme points below forms X - P1 = g u - v
+// directly (differences only), so it carries the relative terms but NOT the lattice term: tol = 1.25 (ds_threads +
+// ds_here) + 1e-6, about half of what two lattice roundings would need on lon/lat coordinates.
 // largest power of two <= x (x > 0, normal)
 __device__ __forceinline__ float pow2_floor(const float x) { return __int_as_float(__float_as_int(x) & 0x7f800000); }
 
@@ -291,8 +292,10 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
             neg += un < 0.f;
             // MUFU-based quotients (relative error < 2^-22 = 4 eps): accounted for in xmag and ds below
             const float g = vn * rcp_approx(un);
-            const float Xx = fmaf(g, ux, pq.x), Xy = fmaf(g, uy, pq.y);
-            const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) * rtt;
+            // X - P1 = g u - v, never formed in absolute coordinates: THIS evaluation then carries relative errors
+            // only, and the lattice rounding of X enters the tolerance once (the threads' evaluation), not twice
+            const float Dx = fmaf(g, ux, -vx), Dy = fmaf(g, uy, -vy);
+            const float s = fmaf(w0.z, Dx, w0.w * Dy) * rtt;
             smin = fminf(smin, s); smax = fmaxf(smax, s);
             gmin = fminf(gmin, g); gmax = fmaxf(gmax, g);
             unmin = fminf(unmin, fabsf(un));
@@ -313,11 +316,14 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         // lattice rounding of X per component: |X_c| <= S_c + |g||u|, and rounding a value of that binade moves it by
         // at most half an ulp = 2^-24 * 2^floor(log2 |X_c|) (not 2^-24 |X_c|: up to 2x tighter, 1.6x at latitude 50.7)
         const float gu1 = gabs * u2m;
-        const float dXx = eps * (pow2_floor(scale_x + gu1) + 0.8f * gu5 + 4.0f * gabs * uxm + amp * uxm) + 1.5f * lip * dev;
-        const float dXy = eps * (pow2_floor(scale_y + gu1) + 0.8f * gu5 + 4.0f * gabs * uym + amp * uym) + 1.5f * lip * dev;
+        // relative-type terms (both evaluations) and the lattice term (the threads' evaluation only)
+        const float relx = eps * (0.8f * gu5 + 4.0f * gabs * uxm + amp * uxm + 2.0f * V1) + 1.5f * lip * dev;
+        const float rely = eps * (0.8f * gu5 + 4.0f * gabs * uym + amp * uym + 2.0f * V1) + 1.5f * lip * dev;
+        const float dXx = eps * pow2_floor(scale_x + gu1) + relx;
+        const float dXy = eps * pow2_floor(scale_y + gu1) + rely;
         const float smag = fmaxf(fabsf(smin), fabsf(smax));
-        const float ds = (fabsf(w0.z) * dXx + fabsf(w0.w) * dXy) * (rtt * 1.000001f) + 8.0f * eps * smag;
-        const float tol = 2.5f * ds + 1e-6f;
+        const float ds = (fabsf(w0.z) * (dXx + relx) + fabsf(w0.w) * (dXy + rely)) * (rtt * 1.000001f) + 16.0f * eps * smag;
+        const float tol = 1.25f * ds + 1e-6f;  // ds = threads' bound + this evaluation's bound
         if (!(tol < CUDART_INF_F)) return true;
         if (i == K - 1) tol_last = tol;  // valid for every point of the tile: reused by warp_may_be_valid
         const float lo = xz - tol, hi = 1.0f - xz + tol;
@@ -394,8 +400,8 @@ __device__ __forceinline__ bool warp_may_be_valid(const float4 w0, const float4 
         const float un = fmaf(ux, w1.x, uy * w1.y);
         const float vn = fmaf(vx, w1.x, vy * w1.y);
         const float g = vn * rcp_approx(un);  // (MUFU quotients: their 2^-22 relative error is a term of `tol`)
-        const float Xx = fmaf(g, ux, px), Xy = fmaf(g, uy, py);
-        const float s = fmaf(w0.z, Xx - w0.x, w0.w * (Xy - w0.y)) * rtt;
+        const float Dx = fmaf(g, ux, -vx), Dy = fmaf(g, uy, -vy);  // X - P1 in relative form, as in the tile-level test
+        const float s = fmaf(w0.z, Dx, w0.w * Dy) * rtt;
         nan = nan || !(s == s);
         smin = fminf(smin, s);
         smax = fmaxf(smax, s);
