@@ -317,10 +317,13 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         // at most half an ulp = 2^-24 * 2^floor(log2 |X_c|) (not 2^-24 |X_c|: up to 2x tighter, 1.6x at latitude 50.7)
         const float gu1 = gabs * u2m;
         // relative-type terms (both evaluations) and the lattice term (the threads' evaluation only)
-        const float relx = eps * (0.8f * gu5 + 4.0f * gabs * uxm + amp * uxm + 2.0f * V1) + 1.5f * lip * dev;
-        const float rely = eps * (0.8f * gu5 + 4.0f * gabs * uym + amp * uym + 2.0f * V1) + 1.5f * lip * dev;
-        const float dXx = eps * pow2_floor(scale_x + gu1) + relx;
-        const float dXy = eps * pow2_floor(scale_y + gu1) + rely;
+        // (the deviation `dev` of the thread's previous point from the point set belongs to the threads' evaluation
+        // only — the evaluation here starts ON the set — so it is counted once as well)
+        const float relx = eps * (0.8f * gu5 + 4.0f * gabs * uxm + amp * uxm + 2.0f * V1);
+        const float rely = eps * (0.8f * gu5 + 4.0f * gabs * uym + amp * uym + 2.0f * V1);
+        const float devterm = 1.5f * lip * dev;
+        const float dXx = eps * pow2_floor(scale_x + gu1) + relx + devterm;
+        const float dXy = eps * pow2_floor(scale_y + gu1) + rely + devterm;
         const float smag = fmaxf(fabsf(smin), fabsf(smax));
         const float ds = (fabsf(w0.z) * (dXx + relx) + fabsf(w0.w) * (dXy + rely)) * (rtt * 1.000001f) + 16.0f * eps * smag;
         const float tol = 1.25f * ds + 1e-6f;  // ds = threads' bound + this evaluation's bound
@@ -349,7 +352,7 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         pts[0] = make_float2(fmaf(a, w0.z, w0.x), fmaf(a, w0.w, w0.y));
         pts[1] = make_float2(fmaf(b, w0.z, w0.x), fmaf(b, w0.w, w0.y));
         npts = 2;
-        dev = 1.25f * fmaxf(dXx, dXy) + 2.0f * eps * S;
+        dev = 1.25f * fmaxf(dXx, dXy) + 1.5f * eps * pow2_floor(S);  // + rounding the two points onto the lattice
     }
     // (A direct test of the FIRST interaction through the unfolded path — s_1 over the images of the box corners —
     // was measured on the bench scenes: it rejected 2 of 100 000 candidates the stage loop had kept, i.e. the
