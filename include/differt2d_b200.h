@@ -183,10 +183,13 @@ int d2d_paths(const D2DProblem *p, float min_valid, int32_t emit_all, D2DPathRec
               unsigned long long *count, void *stream);
 
 /*
- * Host-buffer convenience entry used for end-to-end timing and by callers without device arrays:
- * every pointer of `p` and every output is a HOST pointer; the call stages inputs to the device,
- * runs forward (and backward when any *_bar / want_grad output is non-NULL), copies results back
- * and synchronises `stream` before returning.  `device` is the CUDA ordinal.
+ * Host-buffer entry (numpy users of the reference; `bench.py`'s end-to-end leg): every pointer of `p` and every
+ * output is a HOST pointer (pinned memory lets the copies overlap); the call stages the inputs, runs the forward
+ * kernel and — when any *_bar output is non-NULL — the backward kernel over the activity mask, copies the results
+ * back and synchronises before returning.  2-D grids of >= 2^18 points are traced in row chunks (whole macro tiles,
+ * eight by default, D2D_HOST_CHUNKS=1..16) on three internal streams, so that uploads and downloads overlap the
+ * kernels; Z and grid_bar are bit-identical to the device entries, the scene-parameter cotangents are the sum of the
+ * chunks' partial sums.  Serialised by an internal mutex (one staging arena per process).  `device`: CUDA ordinal.
  */
 int d2d_power_host(const D2DProblem *p, const float *Zbar, float *Z, float *grid_bar,
                    float *objects_bar, float *phis_bar, float *fixed_bar, float *alpha_bar,

@@ -117,6 +117,26 @@ def test_sanitised_scene_drops_closure_walls_and_normalises():
     assert set(unit.transmitters) == set(sc.transmitters) and set(unit.receivers) == set(sc.receivers)
 
 
+def test_bench_reference_arm_prints_one_json_line():
+    """bench.py --impl reference (the CPU arm the driver runs beside ours): exactly ONE line on stdout, valid JSON
+    with the contract's keys — native libraries' banners go to stderr (bench._quiet_stdout)."""
+    import json
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, timeout=600, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference" and line["metric"] == "rx_x_candidate_paths_per_s" and line["value"] > 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["value"] == line["value"]
+    assert "workload" in line["config"] and line["higher_is_better"] is True
+
+
 def test_row_blocks_partition_the_grid():
     for n in (1, 7, 10, 1024, 2048):
         for w in (1, 2, 3, 4, 8):
