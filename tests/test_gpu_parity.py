@@ -821,3 +821,36 @@ def test_scene_api_solver_methods():
     assert np.array_equal(Z2, Z) and dZ.shape == (*X.shape, 2) and np.isfinite(dZ).all() and (dZ != 0).any()
     with pytest.raises(TypeError):
         sc.accumulate_on_receivers_grid_over_paths(X, Y, path_cls=d.MinPath, reduce_all=True, approx=False)
+
+
+# ---- committed golden vectors (last on purpose: everything above has run by the time this one does) -------------------
+@pytest.mark.parametrize("name", ["obstacle", "basic", "geojson", "geojson_norm"])
+def test_cuda_path_against_golden_fixtures(name):
+    """tests/golden/power_fixtures.npz (tests/golden/make_power_fixtures.py; pinned on the CPU tier by
+    test_oracles_reproduce_the_golden_fixtures): hard validity of every (receiver, candidate) and the hard map bit for
+    bit, hard_sigmoid validity bit for bit and maps to 1e-6, the clean VJP (hard_sigmoid, alpha = 20) to 1e-4 of the
+    largest entry — d/d(vertices) is left to the generic-position test (DESIGN.md "Ties")."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "power_fixtures.npz"))
+    X, Y, xys, fixed = g[f"{name}/X"], g[f"{name}/Y"], g[f"{name}/xys"], g[f"{name}/fixed"]
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    shape = tuple(g[f"{name}/hard/valid_shape"])
+    want_v = np.unpackbits(g[f"{name}/hard/valid_bits"])[: int(np.prod(shape))].reshape(shape).astype(np.float32)
+    for tiling in (dict(grid_cols=X.shape[1]), dict(grid_cols=0)):
+        Z, v = F.power_fwd(_cfg("hard", max_order=2, **tiling), xys, fixed, grid, want_valid=True, device="cuda")
+        assert np.array_equal(v.cpu().numpy(), want_v) and np.array_equal(Z.cpu().numpy(), g[f"{name}/hard/Z"])
+    for alpha in (10.0, 100.0):
+        Z, v = F.power_fwd(_cfg("hard_sigmoid", max_order=2, grid_cols=X.shape[1]), xys, fixed, grid, alpha=alpha,
+                           want_valid=True, device="cuda")
+        assert np.array_equal(v.cpu().numpy(), g[f"{name}/hard_sigmoid_{alpha:g}/valid"])
+        np.testing.assert_allclose(Z.cpu().numpy(), g[f"{name}/hard_sigmoid_{alpha:g}/Z"], rtol=1e-6, atol=0)
+    if name == "geojson":
+        return  # (raw lon/lat: every cotangent sits on fp32 noise of the scene itself; the VJP is pinned on the others)
+    out = F.power_bwd(_cfg("hard_sigmoid", max_order=2, reduce_all=True, grid_cols=X.shape[1]), xys, fixed, grid,
+                      g[f"{name}/vjp/Zbar"].reshape(-1), alpha=20.0, device="cuda")
+    out = {k: t.cpu().numpy() for k, t in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), g[f"{name}/vjp/Z"], rtol=1e-5, atol=1e-6)
+    _close(out["grid"].reshape(*X.shape, 2), g[f"{name}/vjp/grid_bar"], 1e-4, "grid_bar")
+    _close(out["fixed"], g[f"{name}/vjp/fixed_bar"], 1e-4, "fixed_bar")
+    _close(out["alpha"], g[f"{name}/vjp/alpha_bar"].reshape(1), 1e-4, "alpha_bar")

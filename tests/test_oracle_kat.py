@@ -293,3 +293,47 @@ def test_clean_gradients_leave_values_unchanged_and_finite():
     assert torch.equal(Z0, Z1)
     assert torch.isnan(g0["grid"]).any()
     assert all(torch.isfinite(v).all() for v in g1.values())
+
+
+# ---- committed golden vectors (tests/golden/power_fixtures.npz, made by tests/golden/make_power_fixtures.py) ----------
+def _golden():
+    import os
+
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "power_fixtures.npz"))
+
+
+@pytest.mark.parametrize("name", ["obstacle", "basic", "geojson", "geojson_norm"])
+def test_oracles_reproduce_the_golden_fixtures(name):
+    """Both restatements (scalar C, torch) still produce the committed vectors: hard validity of every (receiver,
+    candidate) and the hard / hard_sigmoid maps bit for bit, the clean VJP to 1e-6 (torch's threaded reductions)."""
+    import torch
+
+    from oracle import c_oracle as CO
+    from oracle import ref_torch as R
+    from tests import helpers as H
+    from tests.golden import make_power_fixtures as M
+
+    g = _golden()
+    sc = M.scenes()[name]
+    X, Y, xys, fixed = g[f"{name}/X"], g[f"{name}/Y"], g[f"{name}/xys"], g[f"{name}/fixed"]
+    Xn, Yn, xys_n, fixed_n = M.inputs(sc)
+    assert np.array_equal(X, Xn) and np.array_equal(Y, Yn) and np.array_equal(xys, xys_n) and np.array_equal(fixed, fixed_n)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    shape = tuple(g[f"{name}/hard/valid_shape"])
+    want_v = np.unpackbits(g[f"{name}/hard/valid_bits"])[: int(np.prod(shape))].reshape(shape).astype(np.float32)
+    Z, v = CO.power_map(xys, fixed, grid, max_order=2, mode="hard", want_valid=True)
+    assert np.array_equal(v, want_v) and np.array_equal(Z, g[f"{name}/hard/Z"])
+    osc = H.oracle_scene_from_product(sc)
+    _, vt, _ = R.valid_masks(osc, osc.transmitters["tx"], torch.from_numpy(np.stack([X, Y], -1)), max_order=2, approx=False)
+    assert np.array_equal(vt.numpy().reshape(shape[1:]).astype(np.float32), want_v[0])
+    for alpha in (10.0, 100.0):
+        Zs, vs = CO.power_map(xys, fixed, grid, max_order=2, mode="hard_sigmoid", alpha=alpha, want_valid=True)
+        assert np.array_equal(vs, g[f"{name}/hard_sigmoid_{alpha:g}/valid"])
+        assert np.array_equal(Zs, g[f"{name}/hard_sigmoid_{alpha:g}/Z"])
+    with R.clean_gradients():
+        Zo, gr = R.power_map_and_vjp(osc, X, Y, g[f"{name}/vjp/Zbar"], max_order=2, approx=True, alpha=20.0,
+                                     function="hard_sigmoid")
+    np.testing.assert_allclose(Zo.numpy(), g[f"{name}/vjp/Z"], rtol=1e-6, atol=1e-7)
+    for k in ("grid", "xys", "fixed", "alpha"):
+        want = g[f"{name}/vjp/{k}_bar"]
+        np.testing.assert_allclose(gr[k].numpy(), want, rtol=1e-5, atol=1e-6 * max(np.abs(want).max(), 1e-30), err_msg=k)
