@@ -117,6 +117,9 @@ def test_no_cpu_fallback():
     with pytest.raises(d.D2DError):
         F.power_fwd(F.TraceConfig(), np.zeros((1, 2, 2), np.float32), np.zeros((1, 2), np.float32),
                     np.zeros((4, 2), np.float32), device="cpu")
+    with pytest.raises(d.D2DError):  # the host-buffer entry stages to a CUDA device: no device, no result
+        F.power_host(F.TraceConfig(), np.zeros((1, 2, 2), np.float32), np.zeros((1, 2), np.float32),
+                     np.zeros((4, 2), np.float32))
 
 
 def test_product_does_not_import_the_oracle():
