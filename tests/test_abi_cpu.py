@@ -100,6 +100,13 @@ def test_argument_validation_without_gpu():
     # Fermat/MinPath reverse mode needs the x0 table, like the forward
     assert lib.d2d_power_bwd(C.byref(p), None, None, None, None, None, None, None, None) == 1
     assert b"x0" in lib.d2d_last_error()
+    # gradient semantics: clean (default) or nan_parity; the latter covers ImagePath only
+    p.grad_mode = L.GRAD_NAN_PARITY
+    assert lib.d2d_problem_num_candidates(C.byref(p)) == -1 and b"ImagePath" in lib.d2d_last_error()
+    p.method = L.METHOD_IMAGE
+    assert lib.d2d_problem_num_candidates(C.byref(p)) == 785
+    p.grad_mode = 7
+    assert lib.d2d_problem_num_candidates(C.byref(p)) == -1 and b"grad_mode" in lib.d2d_last_error()
 
 
 def test_no_cpu_fallback():
