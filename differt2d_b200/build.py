@@ -95,7 +95,32 @@ def _build(verbose: bool, defs, prefix: str, lib_path: str) -> str:
     return lib_path
 
 
+def build_jax_ffi(verbose: bool = False) -> str:
+    """Compiles jax_ffi/d2d_xla_ffi.cc (the XLA-FFI handlers over the C ABI) against jax.ffi.include_dir().
+    Needs `import jax` to work: not the case in the image this repository was developed in."""
+    try:
+        import jax
+    except ImportError as e:  # loud, never a silent skip
+        raise RuntimeError("--jax-ffi needs JAX (jax.ffi.include_dir() holds the XLA-FFI headers)") from e
+    build()
+    out = os.path.join(OUT_DIR, "libdiffert2d_b200_xla.so")
+    cuda_inc = os.path.join(os.path.dirname(os.path.dirname(_nvcc())), "include") if os.path.isabs(_nvcc()) \
+        else "/usr/local/cuda/include"
+    cmd = ["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-I" + jax.ffi.include_dir(), "-I" + cuda_inc,
+           os.path.join(HERE, "jax_ffi", "d2d_xla_ffi.cc"), "-L" + OUT_DIR, "-ldiffert2d_b200",
+           "-Wl,-rpath,$ORIGIN", "-o", out]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"g++ failed for d2d_xla_ffi.cc:\n{r.stdout}\n{r.stderr}")
+    return out
+
+
 if __name__ == "__main__":
+    if "--jax-ffi" in sys.argv:
+        print(build_jax_ffi(verbose="--verbose" in sys.argv))
+        sys.exit(0)
     path = build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
                  debug_counters="--debug-counters" in sys.argv)
     print(path)
