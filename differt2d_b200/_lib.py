@@ -62,6 +62,8 @@ class D2DProblem(C.Structure):
         ("no_cull", C.c_int32),
         ("candidate_slices", C.c_int32),
         ("active_mask", C.c_void_p),
+        ("cand_shard_index", C.c_int32),
+        ("cand_shard_count", C.c_int32),
         ("many", C.c_int32),
     ]
 
@@ -82,7 +84,7 @@ class D2DPathRecord(C.Structure):
 
 EXPORTS = [
     "d2d_problem_defaults", "d2d_candidates_count", "d2d_candidates_host", "d2d_candidates_device",
-    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_paths", "d2d_power_host", "d2d_launch_count",
+    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_paths", "d2d_power_host", "d2d_host_release", "d2d_launch_count",
     "d2d_fma_peak_launch", "d2d_last_error", "d2d_abi_version",
 ]
 
@@ -122,6 +124,8 @@ def lib() -> C.CDLL:
     L.d2d_power_bwd.restype = C.c_int
     L.d2d_power_host.argtypes = [P, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.d2d_power_host.restype = C.c_int
+    L.d2d_host_release.argtypes = []
+    L.d2d_host_release.restype = None
     L.d2d_launch_count.argtypes = []
     L.d2d_launch_count.restype = C.c_int64
     L.d2d_fma_peak_launch.argtypes = [vp, C.c_int32, C.POINTER(C.c_double), vp]

@@ -5,7 +5,6 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
-#include <mutex>
 #include <string>
 #include <vector>
 
@@ -178,12 +177,17 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
                                          : (p->n_grid + k.tile_points - 1) / k.tile_points;
         if (nblk < 1) nblk = 1;
         long long want = (148LL * 8) / nblk;                      // fill the machine about 8 CTAs deep
-        const long long chunks = (total + 127) / 128;
+        const int shards = p->cand_shard_count > 1 ? p->cand_shard_count : 1;
+        const long long chunks = (total + 127) / 128 / shards;    // (this GPU's share when the list is sharded)
         if (want > chunks / 4) want = chunks / 4;                  // at least 4 chunks per CTA
         if (want > 65535) want = 65535;
         if (want > 1) k.slices = (int)want;
     }
     if (k.slices > 65535) return fail(D2D_ERR_INVALID_ARGUMENT, "candidate_slices must be <= 65535");
+    k.shard_count = p->cand_shard_count > 1 ? p->cand_shard_count : 1;
+    k.shard_index = p->cand_shard_count > 1 ? p->cand_shard_index : 0;
+    if (k.shard_index < 0 || k.shard_index >= k.shard_count)
+        return fail(D2D_ERR_INVALID_ARGUMENT, "need 0 <= cand_shard_index < cand_shard_count");
     // 2-D tiled grids are laid out for thread-block clusters: 8 CTAs = 2 x 4 tiles = one 32 x 32 macro tile whose
     // candidates are culled once, cooperatively, through distributed shared memory (csrc/d2d_driver.cuh)
     k.cluster = (k.grid_cols > 0 && k.slices == 1) ? 8 : 0;
@@ -342,45 +346,75 @@ int d2d_paths(const D2DProblem* p, float min_valid, int32_t emit_all, D2DPathRec
 
 // ---- host-buffer entry ---------------------------------------------------------------------------
 namespace {
-struct DevBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int dev = -1;
-    int ensure(size_t n, int device) {
-        if (n <= cap && dev == device && p) return 0;
-        if (p) cudaFree(p);
-        p = nullptr;
-        cap = 0;
-        const cudaError_t e = cudaMalloc(&p, n < 256 ? 256 : n);
-        if (e != cudaSuccess) return (int)e;
-        cap = n < 256 ? 256 : n;
-        dev = device;
-        return 0;
-    }
-};
-struct PinnedBuf {
-    void* p = nullptr;
-    size_t cap = 0;
-    int ensure(size_t n) {
-        if (n <= cap && p) return 0;
-        if (p) cudaFreeHost(p);
-        p = nullptr;
-        cap = 0;
-        const cudaError_t e = cudaMallocHost(&p, n < 256 ? 256 : n);
-        if (e != cudaSuccess) return (int)e;
-        cap = n < 256 ? 256 : n;
-        return 0;
-    }
-};
 constexpr int kHostStreams = 3;
 constexpr int kHostMaxChunks = 16;
-std::mutex g_host_mu;
-DevBuf g_in, g_out;
-PinnedBuf g_partials;
-cudaStream_t g_host_streams[kHostStreams] = {nullptr, nullptr, nullptr};
-cudaEvent_t g_host_ready = nullptr;
-int g_host_stream_dev = -1;
+
+// Staging state of ONE calling thread on ONE device: arenas grown on demand, three streams, one event.  Nothing here is
+// shared between threads (the entry point is re-entrant without a lock); freed by d2d_host_release() or at thread exit.
+struct HostCtx {
+    int dev = -1;
+    void* din = nullptr;      size_t din_cap = 0;
+    void* dout = nullptr;     size_t dout_cap = 0;
+    void* partials = nullptr; size_t partials_cap = 0;  // pinned
+    cudaStream_t streams[kHostStreams] = {nullptr, nullptr, nullptr};
+    cudaEvent_t ready = nullptr;
+
+    cudaError_t init(int device) {
+        dev = device;
+        cudaError_t e;
+        for (int i = 0; i < kHostStreams; ++i)
+            if ((e = cudaStreamCreateWithFlags(&streams[i], cudaStreamNonBlocking)) != cudaSuccess) return e;
+        return cudaEventCreateWithFlags(&ready, cudaEventDisableTiming);
+    }
+    static cudaError_t grow(void** p, size_t* cap, size_t n, bool pinned) {
+        if (n < 256) n = 256;
+        if (*p && n <= *cap) return cudaSuccess;
+        if (*p) { if (pinned) cudaFreeHost(*p); else cudaFree(*p); }
+        *p = nullptr;
+        *cap = 0;
+        const cudaError_t e = pinned ? cudaMallocHost(p, n) : cudaMalloc(p, n);
+        if (e == cudaSuccess) *cap = n;
+        return e;
+    }
+    void release() {
+        if (dev < 0) return;
+        int cur = -1;
+        const bool sw = cudaGetDevice(&cur) == cudaSuccess && cur != dev && cudaSetDevice(dev) == cudaSuccess;
+        for (auto& s : streams) if (s) { cudaStreamDestroy(s); s = nullptr; }
+        if (ready) { cudaEventDestroy(ready); ready = nullptr; }
+        if (din) cudaFree(din);
+        if (dout) cudaFree(dout);
+        if (partials) cudaFreeHost(partials);
+        din = dout = partials = nullptr;
+        din_cap = dout_cap = partials_cap = 0;
+        if (sw) cudaSetDevice(cur);
+        dev = -1;
+    }
+    ~HostCtx() { release(); }  // (at process exit the driver may already be gone: the calls then fail harmlessly)
+};
+
+struct HostCtxTable {
+    std::vector<HostCtx*> per_dev;
+    ~HostCtxTable() { for (HostCtx* c : per_dev) delete c; }
+};
+thread_local HostCtxTable t_host;
+
+HostCtx* host_ctx(int device, cudaError_t* err) {
+    if (device < 0 || device >= 1024) { *err = cudaErrorInvalidDevice; return nullptr; }
+    if ((size_t)device >= t_host.per_dev.size()) t_host.per_dev.resize((size_t)device + 1, nullptr);
+    HostCtx*& c = t_host.per_dev[(size_t)device];
+    if (!c) {
+        c = new HostCtx();
+        if ((*err = c->init(device)) != cudaSuccess) { delete c; c = nullptr; return nullptr; }
+    }
+    *err = cudaSuccess;
+    return c;
+}
 }  // namespace
+
+void d2d_host_release(void) {
+    for (HostCtx*& c : t_host.per_dev) { delete c; c = nullptr; }
+}
 
 // Large 2-D grids are traced in (eight) row chunks on three streams: the upload of chunk c + 1 and the download of chunk c - 1
 // overlap the kernels of chunk c (the copies are a quarter of a step otherwise: 12.6 MB each way for 1024^2 points).
@@ -389,26 +423,19 @@ int g_host_stream_dev = -1;
 int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* grid_bar, float* objects_bar,
                    float* phis_bar, float* fixed_bar, float* alpha_bar, int32_t device) {
     if (!hp) return fail(D2D_ERR_INVALID_ARGUMENT, "problem is NULL");
-    std::lock_guard<std::mutex> lock(g_host_mu);
     cudaError_t e = cudaSetDevice(device);
     if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    if (!g_host_streams[0] || g_host_stream_dev != device) {
-        for (int i = 0; i < kHostStreams; ++i)
-            if ((e = cudaStreamCreateWithFlags(&g_host_streams[i], cudaStreamNonBlocking)) != cudaSuccess)
-                return cuda_fail(e, "cudaStreamCreate");
-        if ((e = cudaEventCreateWithFlags(&g_host_ready, cudaEventDisableTiming)) != cudaSuccess)
-            return cuda_fail(e, "cudaEventCreate");
-        g_host_stream_dev = device;
-    }
+    HostCtx* cx = host_ctx(device, &e);
+    if (!cx) return cuda_fail(e, "d2d_power_host: stream / event creation");
     const size_t N = (size_t)hp->n_objects, T = (size_t)hp->n_fixed, R = (size_t)hp->n_grid;
     const size_t Tout = hp->reduce_all ? 1 : T;
     D2DProblem dp = *hp;
     dp.alpha_dev = nullptr;
-    if (hp->alpha_dev) dp.alpha = *hp->alpha_dev;  // host scalar in this entry
+    if (hp->alpha_dev) dp.alpha = *hp->alpha_dev;  // host scalar in this entry (validated like `alpha` by pack())
     const long long C = d2d_problem_num_candidates(&dp);
     if (C < 0) return D2D_ERR_INVALID_ARGUMENT;
     const bool want_bwd = grid_bar || objects_bar || phis_bar || fixed_bar || alpha_bar;
-    // chunking: rows in multiples of 32 (whole macro tiles), about a quarter of the grid each
+    // chunking: rows in multiples of 32 (whole macro tiles), about an eighth of the grid each
     int n_chunks = 1;
     size_t chunk_pts = R;
     const size_t cols = (hp->grid_cols > 0 && R % (size_t)hp->grid_cols == 0) ? (size_t)hp->grid_cols : 0;
@@ -433,9 +460,8 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
     const size_t o_xys = 0, o_kind = o_xys + al(N * 16), o_phi = o_kind + al(N), o_fix = o_phi + al(N * 4),
                  o_x0 = o_fix + al(T * 8), o_grid = o_x0 + al(x0_bytes), o_zbar = o_grid + al(R * 8),
                  in_total = o_zbar + (Zbar ? (size_t)n_chunks * al(Tout * chunk_pts * 4) : 0);
-    int rc = g_in.ensure(in_total, device);
-    if (rc) return cuda_fail(rc, "cudaMalloc(inputs)");
-    char* din = (char*)g_in.p;
+    if ((e = HostCtx::grow(&cx->din, &cx->din_cap, in_total, false)) != cudaSuccess) return cuda_fail(e, "cudaMalloc(inputs)");
+    char* din = (char*)cx->din;
     // output arena per chunk: Z | grid_bar | objects_bar | phis_bar | fixed_bar | alpha_bar | mask
     D2DProblem probe = dp;
     probe.n_grid = (int64_t)chunk_pts;
@@ -447,40 +473,51 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
     const size_t q_z = 0, q_gb = q_z + al(Tout * chunk_pts * 4), q_ob = q_gb + al(grid_bar ? Tout * chunk_pts * 8 : 0),
                  q_pb = q_ob + al(N * 16), q_fb = q_pb + al(N * 4), q_ab = q_fb + al(T * 8), q_mask = q_ab + 256,
                  q_total = q_mask + al((size_t)mask_words * 4) + 256;
-    rc = g_out.ensure(q_total * n_chunks, device);
-    if (rc) return cuda_fail(rc, "cudaMalloc(outputs)");
-    char* dout = (char*)g_out.p;
+    if ((e = HostCtx::grow(&cx->dout, &cx->dout_cap, q_total * n_chunks, false)) != cudaSuccess)
+        return cuda_fail(e, "cudaMalloc(outputs)");
+    char* dout = (char*)cx->dout;
     // pinned staging for the per-chunk parameter cotangents
     const size_t part_floats = 5 * N + 2 * T + 1;
     if (n_chunks > 1 && want_bwd) {
-        rc = g_partials.ensure((size_t)n_chunks * part_floats * 4);
-        if (rc) return cuda_fail(rc, "cudaMallocHost(partials)");
+        if ((e = HostCtx::grow(&cx->partials, &cx->partials_cap, (size_t)n_chunks * part_floats * 4, true)) != cudaSuccess)
+            return cuda_fail(e, "cudaMallocHost(partials)");
     }
-    // scene tables on stream 0; the other streams wait for them
-    cudaStream_t s0 = g_host_streams[0];
-    auto h2d = [&](cudaStream_t s, size_t off, const void* src, size_t n) {
-        if (src && n) cudaMemcpyAsync(din + off, src, n, cudaMemcpyHostToDevice, s);
+    // every asynchronous call is checked; after the first failure nothing more is enqueued, the streams are drained
+    // (the caller's buffers must not be in flight when we return) and the error is reported
+    cudaError_t first = cudaSuccess;
+    const char* where = "";
+    auto ck = [&](cudaError_t err, const char* w) {
+        if (err != cudaSuccess && first == cudaSuccess) { first = err; where = w; }
+        return first == cudaSuccess;
     };
+    cudaStream_t s0 = cx->streams[0];
+    auto h2d = [&](cudaStream_t s, size_t off, const void* src, size_t n) {
+        if (src && n && first == cudaSuccess)
+            ck(cudaMemcpyAsync(din + off, src, n, cudaMemcpyHostToDevice, s), "cudaMemcpyAsync(host to device)");
+    };
+    // scene tables on stream 0; the other streams wait for them
     h2d(s0, o_xys, hp->objects_xys, N * 16);
     h2d(s0, o_kind, hp->object_kinds, N);
     h2d(s0, o_phi, hp->object_phis, N * 4);
     h2d(s0, o_fix, hp->fixed_xy, T * 8);
     if (hp->x0) h2d(s0, o_x0, hp->x0, x0_bytes);
-    cudaEventRecord(g_host_ready, s0);
+    if (first == cudaSuccess) ck(cudaEventRecord(cx->ready, s0), "cudaEventRecord");
     dp.objects_xys = (const float*)(din + o_xys);
     dp.object_kinds = hp->object_kinds ? (const uint8_t*)(din + o_kind) : nullptr;
     dp.object_phis = hp->object_phis ? (const float*)(din + o_phi) : nullptr;
     dp.fixed_xy = (const float*)(din + o_fix);
     dp.x0 = hp->x0 ? (const float*)(din + o_x0) : nullptr;
-    for (int c = 0; c < n_chunks; ++c) {
-        cudaStream_t s = g_host_streams[c % kHostStreams];
-        if (s != s0 || c >= kHostStreams) cudaStreamWaitEvent(s, g_host_ready, 0);
+    int rc = D2D_OK;
+    for (int c = 0; c < n_chunks && first == cudaSuccess && rc == D2D_OK; ++c) {
+        cudaStream_t s = cx->streams[c % kHostStreams];
+        if (s != s0 || c >= kHostStreams) { if (!ck(cudaStreamWaitEvent(s, cx->ready, 0), "cudaStreamWaitEvent")) break; }
         const size_t r0 = (size_t)c * chunk_pts, Rc = (r0 + chunk_pts <= R) ? chunk_pts : R - r0;
         char* qo = dout + (size_t)c * q_total;
         const size_t zb_off = o_zbar + (size_t)c * al(Tout * chunk_pts * 4);
         h2d(s, o_grid + r0 * 8, hp->grid_xy ? (const char*)hp->grid_xy + r0 * 8 : nullptr, Rc * 8);
         if (Zbar)
             for (size_t t = 0; t < Tout; ++t) h2d(s, zb_off + t * Rc * 4, Zbar + t * R + r0, Rc * 4);
+        if (first != cudaSuccess) break;
         D2DProblem cp = dp;
         cp.n_grid = (int64_t)Rc;
         cp.grid_xy = (const float*)(din + o_grid + r0 * 8);
@@ -499,7 +536,8 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
         }
         if (rc != D2D_OK) break;
         auto d2h = [&](void* dst, size_t off, size_t n) {
-            if (dst && n) cudaMemcpyAsync(dst, qo + off, n, cudaMemcpyDeviceToHost, s);
+            if (dst && n && first == cudaSuccess)
+                ck(cudaMemcpyAsync(dst, qo + off, n, cudaMemcpyDeviceToHost, s), "cudaMemcpyAsync(device to host)");
         };
         for (size_t t = 0; t < Tout; ++t) {
             if (Z) d2h(Z + t * R + r0, q_z + t * Rc * 4, Rc * 4);
@@ -511,24 +549,22 @@ int d2d_power_host(const D2DProblem* hp, const float* Zbar, float* Z, float* gri
             d2h(fixed_bar, q_fb, T * 8);
             d2h(alpha_bar, q_ab, 4);
         } else if (want_bwd) {
-            float* part = (float*)g_partials.p + (size_t)c * part_floats;
+            float* part = (float*)cx->partials + (size_t)c * part_floats;
             if (objects_bar) d2h(part, q_ob, N * 16);
             if (phis_bar) d2h(part + 4 * N, q_pb, N * 4);
             if (fixed_bar) d2h(part + 5 * N, q_fb, T * 8);
             if (alpha_bar) d2h(part + 5 * N + 2 * T, q_ab, 4);
         }
     }
-    for (int i = 0; i < kHostStreams; ++i) {
-        e = cudaStreamSynchronize(g_host_streams[i]);
-        if (e != cudaSuccess && rc == D2D_OK) rc = cuda_fail(e, "d2d_power_host");
-    }
-    if (rc != D2D_OK) return rc;
+    for (int i = 0; i < kHostStreams; ++i) ck(cudaStreamSynchronize(cx->streams[i]), "cudaStreamSynchronize");
+    if (rc != D2D_OK) return rc;  // (d2d_power_fwd / d2d_power_bwd have set the message)
+    if (first != cudaSuccess) return cuda_fail(first, where);
     if (n_chunks > 1 && want_bwd) {  // partial sums of the chunks, in chunk order
         auto add = [&](float* dst, size_t off, size_t n) {
             if (!dst) return;
             for (size_t i = 0; i < n; ++i) {
                 float acc = 0.0f;
-                for (int c = 0; c < n_chunks; ++c) acc += ((const float*)g_partials.p)[(size_t)c * part_floats + off + i];
+                for (int c = 0; c < n_chunks; ++c) acc += ((const float*)cx->partials)[(size_t)c * part_floats + off + i];
                 dst[i] = acc;
             }
         };

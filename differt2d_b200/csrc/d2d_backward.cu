@@ -405,6 +405,20 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
     const long long r = tile.r;
     const bool active = tile.active;
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
+    if (MODE != D2D_MODE_HARD && !(alpha > 0.0f)) {  // see power_fwd_kernel: every output becomes NaN
+        if (active && blockIdx.y == 0)
+            for (int t = 0; t < (p.reduce_all ? 1 : p.T); ++t) {
+                if (out.Z) out.Z[(long long)t * p.R + r] = CUDART_NAN_F;
+                if (out.grid_bar) reinterpret_cast<float2*>(out.grid_bar)[(long long)t * p.R + r] = make_float2(CUDART_NAN_F, CUDART_NAN_F);
+            }
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            for (int j = threadIdx.x; j < 4 * p.N; j += blockDim.x) if (out.objects_bar) out.objects_bar[j] = CUDART_NAN_F;
+            for (int j = threadIdx.x; j < p.N; j += blockDim.x) if (out.phis_bar) out.phis_bar[j] = CUDART_NAN_F;
+            for (int j = threadIdx.x; j < 2 * p.T; j += blockDim.x) if (out.fixed_bar) out.fixed_bar[j] = CUDART_NAN_F;
+            if (threadIdx.x == 0 && out.alpha_bar) out.alpha_bar[0] = CUDART_NAN_F;
+        }
+        return;
+    }
     if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
         if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
     }

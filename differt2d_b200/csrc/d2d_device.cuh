@@ -48,6 +48,7 @@ struct KParams {
     int grid_cols;         // row length of the grid when it is a row-major n x m mesh (0: unknown)
     int cull;              // tile-level candidate culling on/off (results are identical either way)
     int slices;            // gridDim.y: CTAs sharing one tile, each walking every slices-th chunk of candidates
+    int shard_index, shard_count;  // multi-GPU candidate sharding: this launch owns virtual slices shard_index * slices + y
     int tile_points;       // grid points per CTA when the tile is 1-D (<= kBlock; 1 for point-to-point links)
     int cluster;           // 8: 2-D tiles are numbered cluster by cluster (8 CTAs = 2 x 4 tiles = 32 x 32 points); 0: row-major
     int macro;             // set by a launcher that starts the kernel as clusters of 8 CTAs: macro-tile cull stage on

@@ -603,7 +603,7 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     if constexpr (K == 0) {
         Cand<0> cd;
         cd.c[0] = 0;
-        if (blockIdx.y == 0) visit(cd, col0, fx);  // uniform over the CTA
+        if (blockIdx.y == 0 && p.shard_index == 0) visit(cd, col0, fx);  // uniform over the CTA
         return;
     }
     constexpr int KK = K > 0 ? K : 1;
@@ -716,9 +716,14 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
         r0 = set_before(B0);
         G = (tile.bbox.x <= tile.bbox.z) ? set_before(B0 + Ck) - r0 : 0;  // (a CTA beyond the grid's edge traces nothing)
     }
-    // candidate slices (point-to-point links with huge candidate lists): CTA y walks chunks y, y + slices, ...
+    // candidate slices (point-to-point links with huge candidate lists): CTA y walks chunks y, y + slices, ...;
+    // candidate SHARDS (one per GPU) deal the chunks round robin one level up: virtual slice shard * slices + y of
+    // shards * slices.  The activity mask of a sharded forward only holds this shard's bits, so the mask-driven
+    // backward walks all of them.
+    const long long vs = mread ? (long long)blockIdx.y : (long long)p.shard_index * gridDim.y + blockIdx.y;
+    const long long nvs = mread ? (long long)gridDim.y : (long long)p.shard_count * gridDim.y;
 #pragma unroll 1
-    for (long long g0 = (long long)blockIdx.y * kBlock; g0 < G; g0 += (long long)kBlock * gridDim.y) {
+    for (long long g0 = vs * kBlock; g0 < G; g0 += (long long)kBlock * nvs) {
         const long long g = g0 + tid;
         long long idx = g;
         if (use_macro && g < G) {

@@ -63,6 +63,14 @@ __global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(con
     build_tab(T, p, &sh.count);
     const Tile tile = make_tile(p, T, sh);
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
+    if (MODE != D2D_MODE_HARD && !(alpha > 0.0f)) {
+        // a traced alpha cannot be validated on the host; the folds (act(min x) = min act(x)), the dead-path exits and
+        // the culls all assume a non-decreasing activation: poison the outputs instead of returning wrong numbers
+        // (uniform over the grid: every CTA of a cluster leaves here)
+        if (tile.active && blockIdx.y == 0)
+            for (int t = 0; t < (p.reduce_all ? 1 : p.T); ++t) Z[(long long)t * p.R + tile.r] = CUDART_NAN_F;
+        return;
+    }
     if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
         if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
     }

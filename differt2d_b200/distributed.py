@@ -86,31 +86,97 @@ def shutdown() -> None:
         dist.destroy_process_group()
 
 
+def _current_cuda_device(device=None) -> torch.device:
+    if device is not None:
+        return torch.device(device)
+    if not torch.cuda.is_available():
+        from ._lib import D2DError
+
+        raise D2DError("differt2d_b200 computes on CUDA devices only (no CPU fallback)")
+    return torch.device("cuda", torch.cuda.current_device())
+
+
 def sharded_power_vjp(cfg, xys, fixed, X, Y, Zbar=None, *, alpha=100.0, kinds=None, phis=None, device=None,
                       layout: str = "cyclic"):
     """
-    Row-sharded forward + VJP: this rank traces its rows of the (n, m) grid (`layout="cyclic"`: bands of 8 rows
-    dealt round robin, row_tiles_cyclic; `"block"`: one contiguous block, row_block) and returns its slice of
-    Z / grid_bar plus the ALL-REDUCED scene-parameter cotangents; out["rows"] holds the row indices it owns.
+    Row-sharded forward + VJP: this rank traces its rows of the (n, m) grid (`layout="cyclic"`: bands of 8
+    rows dealt round robin, row_tiles_cyclic; `"block"`: one contiguous block, row_block) with the forward kernel and
+    the mask-driven backward kernel (functional.power_value_and_vjp) and returns its slice of Z / grid_bar plus the
+    ALL-REDUCED scene-parameter cotangents; out["rows"] holds the row indices it owns.
+    Zbar: [n, m] (reduce_all) or [T, n, m]; sliced along the row axis.
     """
+    import dataclasses
+
     from . import functional as F
 
+    device = _current_cuda_device(device)
     world = dist.get_world_size() if dist.is_initialized() else 1
     rank = dist.get_rank() if dist.is_initialized() else 0
-    n = X.shape[0]
+    Xn, Yn = np.asarray(X, dtype=np.float32), np.asarray(Y, dtype=np.float32)
+    n, m = Xn.shape
     if layout == "cyclic":
         rows = row_tiles_cyclic(n, world, rank)
     elif layout == "block":
         rows = np.arange(*row_block(n, world, rank))
     else:
         raise ValueError("layout must be 'cyclic' or 'block'")
-    Xs, Ys = torch.as_tensor(np.asarray(X)[rows]), torch.as_tensor(np.asarray(Y)[rows])
-    grid = torch.stack((Xs, Ys), dim=-1).reshape(-1, 2)
-    zb = None if Zbar is None else torch.as_tensor(np.asarray(Zbar)[rows]).reshape(-1)
-    out = F.power_bwd(cfg, xys, fixed, grid, zb, kinds=kinds, phis=phis, alpha=alpha, device=device)
+    grid = torch.as_tensor(np.stack([Xn[rows], Yn[rows]], -1).reshape(-1, 2)).to(device)
+    zb = None
+    if Zbar is not None:
+        zb_all = np.asarray(Zbar, dtype=np.float32)
+        if zb_all.shape[-2:] != (n, m):
+            raise ValueError(f"Zbar must end with the grid shape {(n, m)}, got {zb_all.shape}")
+        zb = zb_all[..., rows, :].reshape(*zb_all.shape[:-2], -1)  # rows are the second-to-last axis, whatever T
+    cfg = dataclasses.replace(cfg, grid_cols=m)
+    out = F.power_value_and_vjp(cfg, xys, fixed, grid, zb, kinds=kinds, phis=phis, alpha=alpha, device=device)
     n_obj = out["objects"].shape[0]
     buf = pack_param_grads(out["objects"], out["phis"], out["fixed"], out["alpha"])
     allreduce_sum_(buf)
     out["objects"], out["phis"], out["fixed"], out["alpha"] = unpack_param_grads(buf, n_obj, out["fixed"].shape[0])
     out["rows"] = rows
+    return out
+
+
+def candidate_chunks_of_shard(n_candidates: int, slices: int, shard: int, n_shards: int, chunk: int = 128):
+    """
+    Host-side statement of how the kernels deal ONE order's candidate list to candidate shards (csrc/d2d_driver.cuh,
+    for_each_candidate): the list is cut into chunks of 128 candidates; CTA y of shard s walks the chunks q with
+    q % (slices * n_shards) == s * slices + y.  Returns the chunk indices of `shard` (all its CTAs), ascending.
+    Every chunk belongs to exactly one shard; the shards take turns every `slices` chunks (equal work per GPU on the
+    long lists this is meant for).
+    """
+    n_chunks = (int(n_candidates) + chunk - 1) // chunk
+    q = np.arange(n_chunks)
+    v = q % (slices * n_shards)
+    return q[(v >= shard * slices) & (v < (shard + 1) * slices)]
+
+
+def sharded_link_power_vjp(cfg, xys, tx, rx, Zbar=None, *, alpha=100.0, kinds=None, phis=None, x0=None, device=None,
+                           want=("grid", "objects", "phis", "fixed", "alpha")):
+    """
+    Point-to-point links with candidate lists too long for one GPU (500 objects at order 3 are 1.2e8
+    candidates per link): every rank traces ALL (tx, rx) links over ITS share of the candidate list
+    (TraceConfig.cand_shard = (rank, world): chunks of 128 candidates dealt round robin) and ONE all-reduce adds the
+    partial Z [T, R], the partial receiver cotangents [T, R, 2] and the partial scene-parameter cotangents.
+    Returns the dict of functional.power_value_and_vjp with every entry summed over the ranks.
+    """
+    import dataclasses
+
+    from . import functional as F
+
+    device = _current_cuda_device(device)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    cfg = dataclasses.replace(cfg, cand_shard=(rank, world))
+    grid = torch.as_tensor(np.asarray(rx, dtype=np.float32).reshape(-1, 2)).to(device)
+    out = F.power_value_and_vjp(cfg, xys, tx, grid, Zbar, kinds=kinds, phis=phis, alpha=alpha, x0=x0, want=want,
+                                device=device)
+    keys = [k for k in ("Z", "grid", "objects", "phis", "fixed", "alpha") if k in out]
+    buf = torch.cat([out[k].reshape(-1) for k in keys])
+    allreduce_sum_(buf)
+    o = 0
+    for k in keys:
+        n = out[k].numel()
+        out[k] = buf[o:o + n].reshape(out[k].shape)
+        o += n
     return out

@@ -45,6 +45,9 @@ class TraceConfig:
     grid_cols: int = 0  # row length of a row-major mesh grid (enables 16 x 8 tiles); 0 = unknown
     cull: bool = True   # tile-level candidate culling (identical results)
     candidate_slices: int = 0  # 0 = automatic; > 1 splits each tile's candidate list over that many CTAs
+    # (index, count): multi-GPU sharding of the candidate list — this call traces every count-th chunk of 128
+    # candidates; Z and all cotangents are then partial sums to be added over the shards (distributed.py)
+    cand_shard: tuple = (0, 1)
     # "clean": masked branches have zero cotangent.  "nan_parity": additionally NaN wherever jax.grad over the
     # reference's literal graph yields NaN (geometry.py:1105, :227-230, :163-171) — ImagePath only, diagnostic speed
     grad_mode: str = "clean"
@@ -81,10 +84,14 @@ class _Packed:
         self.mask = None
         self.alpha_t = None
         alpha_f = DEFAULT_ALPHA
-        if isinstance(alpha, torch.Tensor):
+        if isinstance(alpha, torch.Tensor) and alpha.device.type == "cuda":
+            # a device scalar (a traced value): not readable without a synchronisation; the kernels return NaN
+            # everywhere when it is not > 0 (include/differt2d_b200.h, alpha_dev)
             self.alpha_t = alpha.detach().to(device=device, dtype=torch.float32).reshape(1).contiguous()
         else:
             alpha_f = float(alpha)
+            if cfg.mode != "hard" and not alpha_f > 0.0:
+                raise L.D2DError(f"alpha must be > 0 (the activations must be non-decreasing), got {alpha_f}")
         self.filter = np.ascontiguousarray(np.asarray(cfg.filter_nodes, dtype=np.int32))
         p = L.new_problem()
         p.n_objects = n
@@ -116,6 +123,7 @@ class _Packed:
         p.grid_cols = int(cfg.grid_cols)
         p.no_cull = 0 if cfg.cull else 1
         p.candidate_slices = int(cfg.candidate_slices)
+        p.cand_shard_index, p.cand_shard_count = int(cfg.cand_shard[0]), int(cfg.cand_shard[1])
         p.grad_mode = GRAD_MODES[cfg.grad_mode]
         self.p = p
         self.T = self.fixed.shape[0]
@@ -245,6 +253,7 @@ def power_host(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phi
     p.fun, p.r_coef, p.height = FUNS[cfg.fun], float(cfg.r_coef), float(cfg.height)
     p.reduce_all, p.grid_cols = int(cfg.reduce_all), int(cfg.grid_cols)
     p.no_cull, p.candidate_slices = (0 if cfg.cull else 1), int(cfg.candidate_slices)
+    p.cand_shard_index, p.cand_shard_count = int(cfg.cand_shard[0]), int(cfg.cand_shard[1])
     p.grad_mode = GRAD_MODES[cfg.grad_mode]
     shapes = {"Z": (Tout, R) if not cfg.reduce_all else (R,), "grid": ((Tout, R, 2) if not cfg.reduce_all else (R, 2)),
               "objects": (N, 2, 2), "phis": (N,), "fixed": (T, 2), "alpha": (1,)}
@@ -374,6 +383,9 @@ def power_map(xys: torch.Tensor, fixed: torch.Tensor, grid: torch.Tensor, *, cfg
     xys = xys.to(dev, torch.float32)
     n = xys.reshape(-1, 2, 2).shape[0]
     phis_t = torch.zeros(n, device=dev) if phis is None else phis.to(dev, torch.float32)
+    if not (isinstance(alpha, torch.Tensor) and alpha.device.type == "cuda"):
+        if cfg.mode != "hard" and not float(alpha) > 0.0:  # (host values are validated here; device scalars in the kernels)
+            raise L.D2DError(f"alpha must be > 0 (the activations must be non-decreasing), got {float(alpha)}")
     alpha_t = alpha if isinstance(alpha, torch.Tensor) else torch.tensor(float(alpha), device=dev)
     alpha_t = alpha_t.to(dev, torch.float32)
     return _PowerMap.apply(xys, phis_t, fixed.to(dev, torch.float32), grid.to(dev, torch.float32), alpha_t, cfg,

@@ -22,6 +22,12 @@ def _xy(a, shape):
     return arr
 
 
+def _tracked(a):
+    """The torch tensor behind a coordinate array when autograd follows it (the analogue of a traced jnp array inside
+    jax.grad: `Point(xy=tx_coords)` in examples/plot_power_optimize.py:84), else None."""
+    return a if (hasattr(a, "requires_grad") and a.requires_grad) else None
+
+
 @dataclass(frozen=True)
 class Point:
     """geometry.py:270-348"""
@@ -29,6 +35,7 @@ class Point:
     xy: np.ndarray = field(default_factory=lambda: np.zeros(2, np.float32))
 
     def __post_init__(self):
+        object.__setattr__(self, "tracked", _tracked(self.xy))
         object.__setattr__(self, "xy", _xy(self.xy, (2,)))
 
     def bounding_box(self):
@@ -56,6 +63,7 @@ class Ray:
     xys: np.ndarray = field(default_factory=lambda: np.array([[0.0, 0.0], [1.0, 0.0]], np.float32))
 
     def __post_init__(self):
+        object.__setattr__(self, "tracked", _tracked(self.xys))
         object.__setattr__(self, "xys", _xy(self.xys, (2, 2)))
 
     def origin(self):
@@ -94,6 +102,11 @@ class RIS(Wall):
 
     phi: float = float(np.pi / 4)
     KIND = L.KIND_RIS
+
+    def __post_init__(self):
+        super().__post_init__()
+        object.__setattr__(self, "tracked_phi", _tracked(self.phi))
+        object.__setattr__(self, "phi", float(self.phi))
 
 
 class Path:
@@ -135,9 +148,11 @@ class MinPath(Path):
 
 
 class PathBatch:
-    """What a generic `fun` receives from the accumulate_* entry points: all emitted paths of ONE order as device
-    tensors (the batched counterpart of the reference's per-path call ``fun(path, *fun_args, **fun_kwargs)``,
-    scene.py:1909).  ``xys`` f32[n, order + 2, 2]; ``valid`` / ``loss`` f32[n]; ``order`` int."""
+    """The ``path`` argument of a generic `fun`: all emitted paths of ONE order as device tensors.  The reference
+    calls ``fun(transmitter, receiver, path, interacting_objects, *fun_args, **fun_kwargs)`` once per path
+    (scene.py:1909-1916, :1318-1325); here the same call is made once per ORDER with every argument batched over the
+    n emitted paths: ``path.xys`` f32[n, order + 2, 2], ``path.valid`` / ``path.loss`` f32[n], ``path.order`` int,
+    ``path.length()`` f32[n] (geometry.py:811-819)."""
 
     def __init__(self, xys, valid, loss, order):
         self.xys, self.valid, self.loss, self.order = xys, valid, loss, int(order)
@@ -145,3 +160,19 @@ class PathBatch:
     def length(self):
         d = (self.xys[:, 1:] - self.xys[:, :-1]) + 1.1920929e-07
         return d.square().sum(-1).sqrt().sum(-1)
+
+
+class PointBatch:
+    """The ``transmitter`` / ``receiver`` argument of a generic `fun`: ``xy`` f32[n, 2] (one row per emitted path)."""
+
+    def __init__(self, xy):
+        self.xy = xy
+
+
+class ObjectBatch:
+    """One entry of the ``interacting_objects`` list of a generic `fun` (``len(interacting_objects)`` is the order, as
+    utils.received_power uses it, utils.py:52): the i-th object of every emitted path — ``index`` i64[n] into
+    Scene.objects, ``xys`` f32[n, 2, 2], ``kind`` u8[n] (0 Wall, 1 RIS, 2 Vertex), ``phi`` f32[n]."""
+
+    def __init__(self, index, xys, kind, phi):
+        self.index, self.xys, self.kind, self.phi = index, xys, kind, phi

@@ -24,12 +24,13 @@ def set_approx(enable: bool) -> None:  # logic.py:68-91
 @contextmanager
 def enable_approx(enable: bool = True):  # logic.py:94-196
     global ENABLE_APPROX
-    with _LOCK:
-        prev = ENABLE_APPROX
-        ENABLE_APPROX = bool(enable)
-        try:
-            yield
-        finally:
+    with _LOCK:  # set and restore under the lock, but never hold it across the with-body (other threads must be
+        prev = ENABLE_APPROX  # able to call set_approx / enable_approx meanwhile; like the reference's jax.config
+        ENABLE_APPROX = bool(enable)  # flag, the switch itself is process-wide)
+    try:
+        yield
+    finally:
+        with _LOCK:
             ENABLE_APPROX = prev
 
 

@@ -23,7 +23,7 @@ import torch
 from . import functional as F
 from . import utils
 from .defaults import DEFAULT_ALPHA, DEFAULT_HEIGHT, DEFAULT_PATCH, DEFAULT_R_COEF
-from .geometry import RIS, FermatPath, ImagePath, MinPath, Path, PathBatch, Point, Vertex, Wall
+from .geometry import RIS, FermatPath, ImagePath, MinPath, ObjectBatch, Path, PathBatch, Point, PointBatch, Vertex, Wall
 from .logic import resolve_mode
 
 
@@ -41,10 +41,11 @@ def _resolve_fun(fun, fun_args, fun_kwargs):
     if fun is utils.length_squared or fun == "length_squared":
         return "length_squared", DEFAULT_R_COEF, DEFAULT_HEIGHT
     if callable(fun):
-        # escape hatch: the paths are materialised by the CUDA kernel and `fun` runs in the host framework on the
-        # batched vertices (PathBatch), see Scene._generic_accumulate
+        # escape hatch: the paths are materialised by the CUDA kernel and `fun` runs in the host framework with the
+        # reference's own signature on batched arguments, see Scene._generic_accumulate
         return "generic", DEFAULT_R_COEF, DEFAULT_HEIGHT
-    raise NotImplementedError("fun must be utils.received_power, utils.length_squared or a callable on PathBatch")
+    raise NotImplementedError("fun must be utils.received_power, utils.length_squared or a callable "
+                              "fun(transmitter, receiver, path, interacting_objects, *fun_args, **fun_kwargs)")
 
 
 def _default_device():
@@ -289,26 +290,72 @@ class Scene:
                             lr=0.1, mode=mode, tol=tol, patch=patch, fun="received_power" if fname == "generic" else fname,
                             r_coef=r_coef, height=height, reduce_all=bool(reduce_all),
                             grad_mode="nan_parity" if nan_parity else "clean")
-        self._generic = fname == "generic"
-        return cfg, alpha
+        return cfg, alpha, fname == "generic"
 
-    def _generic_accumulate(self, cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed, grid, alpha, x0, device):
-        """SURVEY §8 f1 — arbitrary `fun`: Z[t, r] = sum_c valid * fun(path) with the paths materialised by
-        `d2d_paths` (every path whose validity is non-zero) and `fun` evaluated on PathBatch tensors, one call per
-        order.  The summation runs in index order per (t, r) up to the reduction order of index_add_."""
+    def _generic_accumulate(self, cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed, grid, alpha, x0, device,
+                            point_cls=Point):
+        """SURVEY §8 f1 — arbitrary `fun`: Z[t, r] = sum_c valid * fun(transmitter, receiver, path,
+        interacting_objects, *fun_args, **fun_kwargs) (scene.py:1909-1916) with the paths materialised by `d2d_paths`
+        (every path whose validity is non-zero) and `fun` evaluated ONCE PER ORDER on batched arguments (PointBatch,
+        PathBatch, list of ObjectBatch: torch tensors on the device).  `point_cls` is the reference's receiver_cls /
+        transmitter_cls: a custom class is constructed as point_cls(xy=<[n, 2] tensor>) for the grid end of the link.
+        The summation runs in index order per (t, r) up to the reduction order of index_add_."""
         rec = F.paths(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, min_valid=0.0, device=device)
-        T, R = np.asarray(fixed).reshape(-1, 2).shape[0], grid.shape[0]
+        fixed_t = torch.as_tensor(np.asarray(fixed, dtype=np.float32).reshape(-1, 2), device=device)
+        T, R = fixed_t.shape[0], grid.shape[0]
+        xys_t = torch.as_tensor(np.asarray(xys, dtype=np.float32).reshape(-1, 2, 2), device=device)
+        kinds_t = torch.as_tensor(np.asarray(kinds, dtype=np.uint8), device=device)
+        phis_t = torch.as_tensor(np.asarray(phis, dtype=np.float32), device=device)
+        cands = {k: torch.as_tensor(F.candidates(len(self.objects), k, cfg.filter_nodes).astype(np.int64), device=device)
+                 for k in range(max(cfg.min_order, 1), cfg.max_order + 1)}
+        col0, c = {}, 0
+        for k in range(cfg.min_order, cfg.max_order + 1):
+            col0[k] = c
+            c += 1 if k == 0 else int(cands[k].shape[0])
         Z = torch.zeros(T * R, dtype=torch.float32, device=device)
         for k in range(cfg.min_order, cfg.max_order + 1):
             sel = rec["order"] == k
             if not bool(sel.any()):
                 continue
+            fi, gi = rec["fixed"][sel].to(torch.int64), rec["grid"][sel]
             batch = PathBatch(rec["xys"][sel][:, : k + 2], rec["valid"][sel], rec["loss"][sel], k)
-            val = torch.as_tensor(fun(batch, *fun_args, **dict(fun_kwargs or {})), dtype=torch.float32, device=device)
+            fixed_pts = PointBatch(fixed_t[fi])
+            grid_pts = PointBatch(grid[gi]) if point_cls is Point else point_cls(xy=grid[gi])
+            tx, rx = (fixed_pts, grid_pts) if cfg.grid_role == "receivers" else (grid_pts, fixed_pts)
+            objs = []
+            if k > 0:
+                idx = cands[k][rec["candidate"][sel] - col0[k]]  # [n, k] object indices of every emitted path
+                objs = [ObjectBatch(idx[:, i], xys_t[idx[:, i]], kinds_t[idx[:, i]], phis_t[idx[:, i]]) for i in range(k)]
+            val = torch.as_tensor(fun(tx, rx, batch, objs, *fun_args, **dict(fun_kwargs or {})), dtype=torch.float32,
+                                  device=device)
             val = val.expand(batch.valid.shape)
-            Z.index_add_(0, rec["fixed"][sel].to(torch.int64) * R + rec["grid"][sel], batch.valid * val)
+            Z.index_add_(0, fi * R + gi, batch.valid * val)
         Z = Z.reshape(T, R)
         return Z.sum(0) if cfg.reduce_all else Z
+
+    def _tracked_tensors(self, grid_role, device):
+        """torch tensors (objects [N,2,2], phis [N], fixed points [T,2]) that keep the autograd link of every
+        coordinate given as a tensor with requires_grad (Point(xy=t), Wall(xys=t), RIS(phi=t)); None when nothing is
+        tracked.  The analogue of calling the reference's entry points under jax.grad (scene.py:1272-1334 used by
+        examples/plot_power_optimize.py:78-91)."""
+        fixed_src = self.transmitters if grid_role == "receivers" else self.receivers
+        pts = list(fixed_src.values())
+        if not (any(o.tracked is not None or getattr(o, "tracked_phi", None) is not None for o in self.objects)
+                or any(p.tracked is not None for p in pts)):
+            return None
+
+        def t(tracked, value):
+            return (tracked if tracked is not None else torch.as_tensor(value)).to(device=device, dtype=torch.float32)
+
+        if self.objects:
+            xys = torch.stack([t(o.tracked, o.packed_xys()).reshape(2, 2) if not isinstance(o, Vertex)
+                               else t(o.tracked, o.xy).reshape(1, 2).expand(2, 2) for o in self.objects])
+            phis = torch.stack([t(getattr(o, "tracked_phi", None), np.float32(getattr(o, "phi", 0.0))).reshape(())
+                                for o in self.objects])
+        else:
+            xys, phis = torch.zeros((0, 2, 2), device=device), torch.zeros((0,), device=device)
+        fixed = torch.stack([t(p.tracked, p.xy).reshape(2) for p in pts]) if pts else torch.zeros((0, 2), device=device)
+        return xys, phis, fixed
 
     def _x0(self, cfg: F.TraceConfig, key, device):
         """Initial guesses per candidate and restart (optimize.py:132, :173-177); `key` is an int seed or an explicit
@@ -330,9 +377,9 @@ class Scene:
         return x0
 
     def _grid_call(self, grid_role, X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad, path_cls,
-                   path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs):
-        cfg, alpha = self._config(grid_role, fun, fun_args, fun_kwargs, reduce_all, path_cls, path_cls_kwargs,
-                                  min_order, max_order, order, filter_objects, kwargs)
+                   path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs, point_cls=Point):
+        cfg, alpha, generic = self._config(grid_role, fun, fun_args, fun_kwargs, reduce_all, path_cls, path_cls_kwargs,
+                                           min_order, max_order, order, filter_objects, kwargs)
         as_numpy = not isinstance(X, torch.Tensor)
         Xt = torch.as_tensor(np.asarray(X, dtype=np.float32)) if as_numpy else X
         Yt = torch.as_tensor(np.asarray(Y, dtype=np.float32)) if as_numpy else Y
@@ -349,12 +396,26 @@ class Scene:
             cfg = dataclasses.replace(cfg, grid_cols=int(shape[1]))
         back = (lambda t: t.cpu().numpy()) if as_numpy else (lambda t: t.to(Xt.device))
         want_grad = grad or value_and_grad
-        if self._generic and want_grad:
+        if generic and want_grad:
             raise NotImplementedError("gradients of a generic `fun` are not fused; use received_power / length_squared")
+        tracked = None if generic else self._tracked_tensors(grid_role, device)
+        diff = tracked is not None or (isinstance(alpha, torch.Tensor) and alpha.requires_grad) or \
+            (isinstance(X, torch.Tensor) and (X.requires_grad or Y.requires_grad))
+        if diff and not generic and not want_grad:
+            # called under autograd (the analogue of jax.grad over the entry point): differentiable
+            # device tensors come back, in the reference's structure
+            if isinstance(X, torch.Tensor):  # keep the link to X / Y
+                grid = torch.stack((X.to(device, torch.float32), Y.to(device, torch.float32)), dim=-1).reshape(-1, 2)
+            xys_t, phis_t, fixed_t = tracked if tracked is not None else (
+                torch.as_tensor(xys, device=device), torch.as_tensor(phis, device=device), torch.as_tensor(fixed, device=device))
+            Z = F.power_map(xys_t, fixed_t, grid, cfg=cfg, phis=phis_t, alpha=alpha, kinds=kinds, x0=x0)
+            if reduce_all:
+                return Z.reshape(shape)
+            return ((k, Z[i].reshape(shape)) for i, k in enumerate(names))
         if not want_grad:
-            if self._generic:
+            if generic:
                 Z = self._generic_accumulate(cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed, grid, alpha, x0,
-                                             device)
+                                             device, point_cls)
             else:
                 Z = F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, device=device)
             if reduce_all:
@@ -378,7 +439,8 @@ class Scene:
     ):
         """scene.py:1803-1953 — per-transmitter maps over a grid of receivers, keyed by transmitter name."""
         return self._grid_call("receivers", X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad,
-                               path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs)
+                               path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs,
+                               receiver_cls)
 
     def accumulate_on_transmitters_grid_over_paths(
         self, X, Y, fun=utils.received_power, fun_args: tuple = (), fun_kwargs: Optional[Mapping[str, Any]] = None, *,
@@ -388,12 +450,13 @@ class Scene:
     ):
         """scene.py:1489-1648 — per-receiver maps over a grid of transmitters, keyed by receiver name."""
         return self._grid_call("transmitters", X, Y, fun, fun_args, fun_kwargs, reduce_all, grad, value_and_grad,
-                               path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs)
+                               path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs,
+                               transmitter_cls)
 
     def _materialise(self, path_cls, path_cls_kwargs, min_order, max_order, order, filter_objects, key, kwargs,
                      emit_all: bool, min_valid: float = 0.5):
-        cfg, alpha = self._config("receivers", utils.received_power, (), None, False, path_cls, path_cls_kwargs,
-                                  min_order, max_order, order, filter_objects, kwargs)
+        cfg, alpha, _ = self._config("receivers", utils.received_power, (), None, False, path_cls, path_cls_kwargs,
+                                     min_order, max_order, order, filter_objects, kwargs)
         device = _default_device()
         tx_names, rx_names = list(self.transmitters), list(self.receivers)
         if not tx_names or not rx_names:
@@ -457,8 +520,8 @@ class Scene:
         NB the reference draws one PRNG key per (pair, candidate) here (scene.py:1209-1212); this mirror
         uses the per-candidate table of the grid methods for every pair.
         """
-        cfg, alpha = self._config("receivers", fun, fun_args, fun_kwargs, False, path_cls, path_cls_kwargs,
-                                  min_order, max_order, order, filter_objects, kwargs)
+        cfg, alpha, generic = self._config("receivers", fun, fun_args, fun_kwargs, False, path_cls, path_cls_kwargs,
+                                           min_order, max_order, order, filter_objects, kwargs)
         device = _default_device()
         tx_names, rx_names = list(self.transmitters), list(self.receivers)
         fixed = np.stack([self.transmitters[k].xy for k in tx_names]) if tx_names else np.zeros((0, 2), np.float32)
@@ -467,7 +530,24 @@ class Scene:
         x0 = self._x0(cfg, key, device)
         if not tx_names or not rx_names:
             return np.float32(0.0) if reduce_all else iter(())
-        if self._generic:
+        tracked = None if generic else self._tracked_tensors("receivers", device)
+        rx_tracked = any(p.tracked is not None for p in self.receivers.values())
+        if tracked is not None or rx_tracked or (isinstance(alpha, torch.Tensor) and alpha.requires_grad):
+            # under autograd (jax.value_and_grad(loss) in examples/plot_power_optimize.py:78-91): differentiable
+            # 0-dim device tensors, accumulated like the reference (acc = 0.0; Z = Z + p, scene.py:1305-1334)
+            xys_t, phis_t, fixed_t = tracked if tracked is not None else (
+                torch.as_tensor(xys, device=device), torch.as_tensor(phis, device=device), torch.as_tensor(fixed, device=device))
+            grid_t = torch.stack([(p.tracked if p.tracked is not None else torch.as_tensor(p.xy)).to(device, torch.float32)
+                                  for p in self.receivers.values()])
+            Zt = F.power_map(xys_t, fixed_t, grid_t, cfg=cfg, phis=phis_t, alpha=alpha, kinds=kinds, x0=x0)
+            if reduce_all:
+                total = torch.zeros((), device=device)
+                for i in range(len(tx_names)):
+                    for j in range(len(rx_names)):
+                        total = total + Zt[i, j]
+                return total
+            return ((t, r, Zt[i, j]) for i, t in enumerate(tx_names) for j, r in enumerate(rx_names))
+        if generic:
             Z = self._generic_accumulate(cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed,
                                          torch.as_tensor(grid).to(device), alpha, x0, device).cpu().numpy()
         else:

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define D2D_ABI_VERSION 2
+#define D2D_ABI_VERSION 3
 
 /* limits of this build */
 #define D2D_MAX_ORDER 4      /* interactions per path (reference examples use <= 3) */
@@ -93,7 +93,10 @@ typedef struct D2DProblem {
     /* ---- validity logic: Path.is_valid (geometry.py:908-963) --------------------------------- */
     int32_t mode;           /* D2D_MODE_*                                                         */
     float alpha;            /* activation slope (defaults.py:3); must be > 0                      */
-    const float *alpha_dev; /* optional device scalar overriding `alpha` (a traced jnp scalar)    */
+    const float *alpha_dev; /* optional device scalar overriding `alpha` (a traced jnp scalar).   */
+                            /* It cannot be validated on the host without a synchronisation: a    */
+                            /* value that is not > 0 makes every output of the call NaN (the folds */
+                            /* and culls assume a non-decreasing activation)                       */
     float tol;              /* loss tolerance of is_valid (geometry.py:915), default 1e-2         */
     float patch;            /* wall lengthening for the occlusion test (geometry.py:632-635)      */
     /* ---- accumulated function --------------------------------------------------------------- */
@@ -103,15 +106,23 @@ typedef struct D2DProblem {
     int32_t reduce_all; /* sum over the fixed points (scene.py:1939-1952)                          */
     int32_t grad_mode;  /* D2D_GRAD_*                                                              */
     int32_t no_cull;    /* 1 disables the tile-level candidate culling (identical results, slower)        */
-    int32_t candidate_slices; /* 0 = automatic.  > 1: that many CTAs share each tile's candidate list and combine  */
-                              /* their partial sums with fp32 atomics (point-to-point links with huge lists, e.g.  */
-                              /* 500 objects at order 3); the summation order of Z is then not the list order.     */
+    int32_t candidate_slices; /* 0 = automatic (lists of >= 16384 candidates on few tiles).  > 1: that many CTAs share  */
+                              /* each tile's candidate list and combine their partial sums with fp32 atomics (point-to- */
+                              /* point links with huge lists, e.g. 500 objects at order 3): the summation order of Z    */
+                              /* and grid_bar is then NOT the list order and NOT reproducible from run to run (last-bit */
+                              /* differences); 1 forces the ordered, bit-reproducible single-CTA walk.                  */
     uint32_t *active_mask; /* optional DEVICE buffer of d2d_active_mask_words(p) words: the custom_vjp RESIDUAL.       */
                            /* d2d_power_fwd fills it with one bit per (fixed point, warp of 32 grid points, candidate):  */
                            /* "some path of this group has a non-zero validity".  d2d_power_bwd, given the buffer a    */
                            /* forward over the SAME inputs filled, re-traces only the set bits instead of the whole     */
                            /* candidate list (identical results; the reference keeps a full tape of every intermediate */
                            /* at [n,m] size instead, scene.py:1920-1952).  NULL: the backward re-traces everything.     */
+    int32_t cand_shard_index; /* multi-GPU sharding of the CANDIDATE list (point-to-point links with huge lists, SURVEY    */
+    int32_t cand_shard_count; /* §8e): this call walks chunk (of 128 candidates) number q of every order only when      */
+                              /* q % (slices * cand_shard_count) falls into shard cand_shard_index (chunks are dealt     */
+                              /* round robin: equal work per rank); order 0 belongs to shard 0.  Z and every cotangent  */
+                              /* are then PARTIAL sums: the caller adds them over the shards (one all-reduce).           */
+                              /* 0 or 1 = the whole list.                                                                */
     int32_t many; /* Fermat/MinPath restarts, optimize.py:142-182 (minimize_many_random_uniform): the scan runs    */
                   /* `many` times from x0[c, 0..many-1] and the iterate with the smallest final loss is kept       */
                   /* (first one on ties, jnp.argmin).  0 or 1 = a single run (the path classes' default, :1198).   */
@@ -189,11 +200,16 @@ int d2d_paths(const D2DProblem *p, float min_valid, int32_t emit_all, D2DPathRec
  * back and synchronises before returning.  2-D grids of >= 2^18 points are traced in row chunks (whole macro tiles,
  * eight by default, D2D_HOST_CHUNKS=1..16) on three internal streams, so that uploads and downloads overlap the
  * kernels; Z and grid_bar are bit-identical to the device entries, the scene-parameter cotangents are the sum of the
- * chunks' partial sums.  Serialised by an internal mutex (one staging arena per process).  `device`: CUDA ordinal.
+ * chunks' partial sums.  `device`: CUDA ordinal.
+ * Re-entrant and thread-safe: the staging arenas, streams and the event belong to the CALLING THREAD (one set per
+ * thread and device, grown on demand and reused by that thread's later calls); no lock is taken and no state is
+ * shared between threads.  d2d_host_release() frees the calling thread's arenas (they are also freed at thread exit).
  */
 int d2d_power_host(const D2DProblem *p, const float *Zbar, float *Z, float *grid_bar,
                    float *objects_bar, float *phis_bar, float *fixed_bar, float *alpha_bar,
                    int32_t device);
+
+void d2d_host_release(void);
 
 /* Kernel launches issued by this library since load (for the bench's gpu_launches claim). */
 int64_t d2d_launch_count(void);

@@ -35,8 +35,9 @@ from typing import Iterable, Optional, Sequence
 import numpy as np
 import torch
 
-F32 = torch.float32
-EPS32 = float(np.finfo(np.float32).eps)  # geometry.py:200  jnp.finfo(dtype).eps
+F32 = torch.float32  # the WORKING dtype (name kept from the fp32-only version); see `precision`
+_NP = np.float32
+EPS32 = float(np.finfo(np.float32).eps)  # geometry.py:200  jnp.finfo(dtype).eps — the fp32 value in BOTH precisions
 
 KIND_WALL, KIND_RIS, KIND_VERTEX = 0, 1, 2
 
@@ -58,6 +59,35 @@ P0 = 100.0
 CLEAN = False
 
 
+class precision:
+    """
+    ``with precision("f64"):`` evaluates the SAME function of the SAME fp32 inputs in binary64 (inputs are
+    rounded to fp32 first, then widened; literal constants 0.005, 1e-2, eps, r_coef**k, height**2 keep their
+    fp32 values).  Not a model of the reference (which is fp32 throughout, docs/source/contributing/
+    internals.md:7-10): it is the third leg of the parity triangulation — where the fp32 and fp64 evaluations
+    of the oracle disagree, the quantity is ill-conditioned in fp32 and no two fp32 implementations (XLA's FMA
+    contraction, this oracle, the CUDA kernels) can be expected to agree there (tests/test_gpu_parity.py).
+    """
+
+    def __init__(self, name: str = "f64"):
+        assert name in ("f32", "f64")
+        self.dt, self.np = (torch.float64, np.float64) if name == "f64" else (torch.float32, np.float32)
+
+    def __enter__(self):
+        global F32, _NP
+        self.prev = (F32, _NP)
+        F32, _NP = self.dt, self.np
+
+    def __exit__(self, *a):
+        global F32, _NP
+        F32, _NP = self.prev
+
+
+def _c(x: float) -> torch.Tensor:
+    """A literal constant of the reference: its fp32 value, in the working dtype."""
+    return torch.tensor(float(np.float32(x)), dtype=F32)
+
+
 class clean_gradients:
     def __init__(self, on: bool = True):
         self.on = on
@@ -75,7 +105,7 @@ class clean_gradients:
 def _t(x, requires_grad: bool = False) -> torch.Tensor:
     if isinstance(x, torch.Tensor):
         return x.to(F32)
-    return torch.tensor(np.asarray(x, dtype=np.float32), dtype=F32, requires_grad=requires_grad)
+    return torch.tensor(np.asarray(x, dtype=np.float32), dtype=F32, requires_grad=requires_grad)  # fp32 values, widened
 
 
 # ----------------------------------------------------------------------------
@@ -182,7 +212,7 @@ class _SqrtDiff(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x):
-        y = torch.from_numpy(np.asarray(np.sqrt(x.detach().contiguous().numpy()), dtype=np.float32))
+        y = torch.from_numpy(np.asarray(np.sqrt(x.detach().contiguous().numpy()), dtype=_NP))
         ctx.save_for_backward(x)
         return y
 
@@ -197,7 +227,7 @@ class _SqrtDiff(torch.autograd.Function):
 def _sqrt(x):
     if x.requires_grad and torch.is_grad_enabled():
         return _SqrtDiff.apply(x)
-    return torch.from_numpy(np.asarray(np.sqrt(x.detach().contiguous().numpy()), dtype=np.float32))
+    return torch.from_numpy(np.asarray(np.sqrt(x.detach().contiguous().numpy()), dtype=_NP))
 
 
 # ----------------------------------------------------------------------------
@@ -238,7 +268,7 @@ def path_length(points):
 
 def segments_intersect(P1, P2, P3, P4, logic: Logic, tol=0.005):
     """geometry.py:82-173 (Graphics Gems III).  All points broadcast over leading dims."""
-    tol = torch.tensor(tol, dtype=F32)
+    tol = _c(tol)
     A = P2 - P1
     B = P3 - P4
     C = P1 - P3
@@ -280,6 +310,12 @@ class OScene:
     @property
     def n(self):
         return self.xys.shape[0]
+
+    def cast(self):
+        """The same scene with its tensors in the working dtype (see `precision`)."""
+        if self.xys.dtype == F32:
+            return self
+        return OScene(self.xys.detach(), self.kinds, self.phis.detach(), self.transmitters, self.receivers)
 
     # Ray.origin/dest/t : geometry.py:458-487
     def origin(self, j):
@@ -506,8 +542,8 @@ def minimize_adam(fun, x0, steps=100, lr=0.1, differentiable=False):
             x = xg.detach()
         mu = (1 - b1) * g + b1 * mu
         nu = (1 - b2) * (g * g) + b2 * nu
-        bc1 = np.float32(1) - np.float32(b1) ** np.float32(count)
-        bc2 = np.float32(1) - np.float32(b2) ** np.float32(count)
+        bc1 = _NP(1) - _NP(b1) ** _NP(count)
+        bc2 = _NP(1) - _NP(b2) ** _NP(count)
         mu_hat = mu / float(bc1)
         nu_hat = nu / float(bc2)
         upd = mu_hat / (torch.sqrt(nu_hat) + eps)
@@ -633,7 +669,7 @@ def is_valid(scene: OScene, cand, xys, loss, logic: Logic, tol=1e-2, patch=DEFAU
     v = logic.lall(
         on_objects(scene, cand, xys, logic),
         logic.lnot(intersects_with_objects(scene, cand, xys, logic, patch)),
-        logic.lt(loss, torch.tensor(tol, dtype=F32)),
+        logic.lt(loss, _c(tol)),
     )
     if v.dtype.is_floating_point:
         v = torch.nan_to_num(v)
@@ -689,6 +725,7 @@ def accumulate_on_grid(
     "transmitters".  Returns a list of (name, Z | dZ | (Z, dZ)) or the reduced arrays.
     """
     fun_kwargs = fun_kwargs or {}
+    scene = scene.cast()
     logic = Logic(approx, alpha, function)
     cands = all_path_candidates(scene.n, min_order, max_order, order=order, filter_nodes=filter_nodes)
     X = _t(X)
@@ -744,6 +781,7 @@ def power_map_and_vjp(
     for a given Zbar [n,m] (default: ones).
     """
     fun_kwargs = fun_kwargs or {}
+    scene = scene.cast()
     X = _t(X)
     Y = _t(Y)
     grid = torch.stack((X, Y), dim=-1).detach().clone().requires_grad_(True)
@@ -785,6 +823,7 @@ def valid_masks(scene: OScene, tx, rx, *, method="image", min_order=0, max_order
                 x0=None, steps=100, lr=0.1, approx=False, alpha=DEFAULT_ALPHA, function="hard_sigmoid",
                 patch=DEFAULT_PATCH, tol=1e-2, fun="received_power", fun_kwargs=None):
     """Per-candidate (valid, fun value) for broadcastable tx / rx — the parity probe."""
+    scene = scene.cast()
     logic = Logic(approx, alpha, function)
     cands = all_path_candidates(scene.n, min_order, max_order, filter_nodes=filter_nodes)
     collect = []

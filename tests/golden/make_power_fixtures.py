@@ -1,6 +1,6 @@
 """
 Generates tests/golden/power_fixtures.npz: golden vectors of the hot path on small seeded inputs, produced by the CPU
-oracle (oracle/d2d_oracle.c for masks and maps, oracle/ref_torch.py + autograd for the clean VJP).  The reference itself
+oracle (oracle/d2d_oracle.c for masks and maps, oracle/ref_torch.py + autograd for the clean VJP, in fp32 and in fp64).  The reference itself
 cannot run in this image (no JAX), so these pin the ORACLE: tests/test_oracle_kat.py::test_oracles_reproduce_the_golden_
 fixtures checks that both restatements still reproduce them bit for bit, tests/test_gpu_parity.py::test_cuda_path_
 against_golden_fixtures checks the CUDA path against the same arrays.
@@ -61,6 +61,14 @@ def compute(name, sc):
     out[f"{name}/vjp/Z"] = Zo.numpy()
     for k in ("grid", "xys", "fixed", "alpha"):
         out[f"{name}/vjp/{k}_bar"] = g[k].numpy()
+    # the same VJP evaluated in binary64 on the same fp32 inputs (ref_torch.precision): where it differs from the
+    # fp32 value the quantity is ill-conditioned in fp32 (third leg of the parity triangulation)
+    with R.clean_gradients(), R.precision("f64"):
+        Z64, g64 = R.power_map_and_vjp(H.oracle_scene_from_product(sc), X, Y, Zbar, max_order=2, approx=True,
+                                       alpha=20.0, function="hard_sigmoid")
+    out[f"{name}/vjp64/Z"] = Z64.numpy()
+    for k in ("grid", "xys", "fixed", "alpha"):
+        out[f"{name}/vjp64/{k}_bar"] = g64[k].numpy()
     return out
 
 

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), f"{n} is declared in include/differt2d_b200.h but not exported"
     assert sorted(L.EXPORTS) == names
-    assert lib.d2d_abi_version() == 2
+    assert lib.d2d_abi_version() == 3
 
 
 def test_struct_layout_matches_header_order():

@@ -80,7 +80,7 @@ def test_hard_masks_and_map_bit_exact(name, grid_kind, tiling):
 
 @pytest.mark.parametrize("name", ["obstacle", "basic", "geojson", "geojson_norm"])
 @pytest.mark.parametrize("mode", ["hard_sigmoid", "sigmoid"])
-@pytest.mark.parametrize("alpha", [1.0, 10.0, 100.0, 1000.0])
+@pytest.mark.parametrize("alpha", [1.0, 10.0, 50.0, 100.0, 1000.0])  # BASELINE config 2's sweep
 def test_smooth_validity_and_map(name, mode, alpha):
     sc = SCENES[name]
     X, Y = _grid(sc, 32, 36, "bbox")
@@ -123,12 +123,40 @@ def _oracle_vjp(sc, X, Y, Zbar, mode, alpha, role="receivers", max_order=2):
                                    alpha=alpha, function="sigmoid" if mode == "sigmoid" else "hard_sigmoid")
 
 
-def _close(got, want, rtol, what):
+def _close(got, want, rtol, what, want64=None, max_escaped=0.10):
+    """
+    ELEMENTWISE comparison, the bar north_star states: |got - want| <= rtol |want| + 1e-6 max|want| for every entry.
+    `want64` (an array, or a callable producing it lazily): the same oracle evaluated in binary64 on the same fp32
+    inputs (ref_torch.precision).  Entries that miss the bar are then still accepted when the fp32 ORACLE ITSELF is
+    no closer to the fp64 value there — |got - want| <= 4 |want - want64| + 4 P90(|want - want64|) — i.e. the
+    quantity is ill-conditioned in fp32 and two correct fp32 evaluations cannot agree; the number of such entries is
+    bounded (max_escaped) and printed.  Without want64 there is no escape.
+    """
     got = np.asarray(got, np.float64)
-    want = np.asarray(want, np.float64)
+    want = np.asarray(want, np.float64).reshape(got.shape)
     scale = max(np.abs(want).max(), 1e-30)
-    err = np.abs(got - want).max() / scale
-    assert err <= rtol, f"{what}: max |diff| / max |want| = {err:.3e} > {rtol:g}"
+    tol = rtol * np.abs(want) + 1e-6 * scale
+    bad = np.abs(got - want) > tol
+    if not bad.any():
+        return 0
+    worst = np.unravel_index(np.argmax(np.abs(got - want) - tol), got.shape)
+    msg = (f"{what}: {int(bad.sum())} of {bad.size} entries miss rtol {rtol:g} (+1e-6 max|want|); worst at {worst}: "
+           f"got {got[worst]:.9g} want {want[worst]:.9g}; max|want| {scale:.3g}")
+    assert want64 is not None, msg
+    w64 = np.asarray(want64() if callable(want64) else want64, np.float64).reshape(got.shape)
+    noise = np.abs(want - w64)
+    tol2 = tol + 4.0 * noise + 4.0 * np.percentile(noise, 90)
+    still = np.abs(got - want) > tol2
+    assert not still.any(), msg + f"; {int(still.sum())} of them also exceed the oracle's own fp32-vs-fp64 distance"
+    frac = bad.sum() / bad.size
+    assert frac <= max_escaped, msg + f"; all within the oracle's own fp32-vs-fp64 distance, but {frac:.1%} > {max_escaped:.0%}"
+    print(f"[parity] {what}: {int(bad.sum())} of {bad.size} entries accepted through the fp64 triangulation")
+    return int(bad.sum())
+
+
+def _oracle_vjp64(*a, **kw):
+    with R.precision("f64"):
+        return _oracle_vjp(*a, **kw)
 
 
 @pytest.mark.parametrize("name", ["obstacle", "basic", "geojson_norm"])
@@ -144,6 +172,15 @@ def test_vjp_against_autograd_oracle(name, mode, alpha, generic):
     rng = np.random.default_rng(7)
     Zbar = rng.standard_normal(X.shape).astype(np.float32)
     Zo, go = _oracle_vjp(sc, X, Y, Zbar, mode, alpha)
+    cache = {}
+
+    def g64(key):  # the fp64 leg is only evaluated when an entry misses the elementwise bar
+        def f():
+            if "g" not in cache:
+                cache["g"] = _oracle_vjp64(sc, X, Y, Zbar, mode, alpha)[1]
+            return cache["g"][key].numpy()
+        return f
+
     xys, kinds, phis = sc.packed_objects()
     fixed = np.stack([p.xy for p in sc.transmitters.values()])
     grid = np.stack([X, Y], -1).reshape(-1, 2)
@@ -151,12 +188,14 @@ def test_vjp_against_autograd_oracle(name, mode, alpha, generic):
                       Zbar.reshape(-1), alpha=alpha, device="cuda")
     out = {k: v.cpu().numpy() for k, v in out.items()}
     np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
-    _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar")
-    _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar")
+    _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar", g64("grid"))
+    _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar", g64("fixed"), max_escaped=1.0)
+    # d/d(vertices): on the axis-aligned canned scenes the smooth-logic sub-gradient sits on STRUCTURAL min/max ties
+    # (DESIGN.md "Ties": ta + tb == 1 on whole regions), compared on the generic-position variants
     if generic or mode == "hard":
-        _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar")
+        _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar", g64("xys"), max_escaped=0.25)
     if mode != "hard":
-        _close(out["alpha"], go["alpha"].numpy().reshape(1), 1e-4, "alpha_bar")
+        _close(out["alpha"], go["alpha"].numpy().reshape(1), 1e-4, "alpha_bar", g64("alpha"), max_escaped=1.0)
     else:
         assert out["alpha"][0] == 0.0
 
@@ -780,21 +819,42 @@ def test_paths_records_reproduce_the_forward_map(mode):
 
 
 def test_generic_fun_escape_hatch():
-    """an arbitrary `fun` evaluated on PathBatch tensors gives the fused kernel's map when it restates
-    utils.received_power (rtol 1e-6: summation order of index_add_), and the reference's LOS KAT for length**2."""
+    """an arbitrary `fun` with the REFERENCE'S signature fun(transmitter, receiver, path,
+    interacting_objects, *fun_args, **fun_kwargs) (scene.py:1909-1916), evaluated on batched arguments, gives the fused
+    kernel's map when it restates utils.received_power (utils.py:52-54; rtol 1e-6: summation order of index_add_),
+    and the reference's LOS KAT for length**2."""
     sc = SCENES["obstacle"]
     X, Y = _grid(sc, 30, 28, "jitter")
+    seen = {}
 
-    def my_power(paths, r_coef=0.5, height=0.1):
-        r = paths.length()
-        return (r_coef ** paths.order) / (height * height + r * r)
+    def my_power(transmitter, receiver, path, interacting_objects, r_coef=0.5, height=0.1):
+        r = path.length()
+        n = len(interacting_objects)
+        seen[n] = (transmitter.xy.shape, receiver.xy.shape, [o.xys.shape for o in interacting_objects])
+        if n:  # the batched objects are the scene's: the path's interaction points lie on their supporting lines
+            o = interacting_objects[0]
+            t = o.xys[:, 1] - o.xys[:, 0]
+            w = path.xys[:, 1] - o.xys[:, 0]
+            cross = t[:, 0] * w[:, 1] - t[:, 1] * w[:, 0]
+            assert float(cross.abs().max()) < 1e-5
+        return (r_coef ** n) / (height * height + r * r)
 
     for approx in (False, True):
         got = sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=my_power, reduce_all=True, max_order=2, approx=approx)
         want = sc.accumulate_on_receivers_grid_over_paths(X, Y, reduce_all=True, max_order=2, approx=approx)
         np.testing.assert_allclose(got, want, rtol=2e-6, atol=1e-7)
+    assert set(seen) == {0, 1, 2} and seen[2][0][1] == 2 and seen[2][0] == seen[2][1] and len(seen[2][2]) == 2
+    Xr, Yr = X[:4, :5], Y[:4, :5]
+    sc2 = sc.update_receivers(rx2=d.Point(xy=[0.8, 0.3]))
+    got = dict(sc2.accumulate_on_transmitters_grid_over_paths(Xr, Yr, fun=my_power, max_order=2, approx=False))
+    want = dict(sc2.accumulate_on_transmitters_grid_over_paths(Xr, Yr, max_order=2, approx=False))
+    assert list(got) == ["rx", "rx2"]
+    for k in got:
+        np.testing.assert_allclose(got[k], want[k], rtol=2e-6, atol=1e-7)
+    tot = sc2.accumulate_over_paths(fun=my_power, reduce_all=True, max_order=2, approx=False)
+    np.testing.assert_allclose(tot, sc2.accumulate_over_paths(reduce_all=True, max_order=2, approx=False), rtol=2e-6)
     res = list(d.Scene.square_scene().accumulate_on_receivers_grid_over_paths(
-        X, Y, fun=lambda p, s: s * p.length() ** 2, fun_args=(2.0,), max_order=0, approx=False))
+        X, Y, fun=lambda tx, rx, p, objs, s: s * p.length() ** 2, fun_args=(2.0,), max_order=0, approx=False))
     assert [k for k, _ in res] == ["tx"]
     np.testing.assert_allclose(res[0][1], 2.0 * ((X - 0.2) ** 2 + (Y - 0.2) ** 2), rtol=1e-5, atol=1e-6)
     with pytest.raises(NotImplementedError):

@@ -1,0 +1,450 @@
+"""
+GPU parity tests, second batch ("Next round" item 1): the configuration bench.py times (raw lon/lat
+city scene) against the autograd oracle with an fp64 third leg, the transmitters-grid role against the oracle (smooth
+forward and full VJP), RIS objects inside ImagePath, non-default `received_power` parameters.
+
+Bars (BASELINE.json north_star): hard and hard_sigmoid validity bit-exact; maps rtol 1e-5; gradients ELEMENTWISE
+rtol 1e-4 (+ 1e-6 of the largest entry), see test_gpu_parity._close.
+"""
+import numpy as np
+import pytest
+import torch
+
+import differt2d_b200 as d
+from differt2d_b200 import functional as F
+from oracle import c_oracle as CO
+from oracle import ref_torch as R
+from tests import helpers as H
+from tests.test_gpu_parity import SCENES, _cfg, _close, _oracle_vjp, _oracle_vjp64
+
+pytestmark = pytest.mark.gpu
+
+FN = {"hard": "hard_sigmoid", "hard_sigmoid": "hard_sigmoid", "sigmoid": "sigmoid"}
+
+
+def _bench_subgrid(sc, n=13, m=12):
+    """n x m points of the 1024 x 1024 bbox grid bench.py traces (every 79th row from 5, every 89th column from 11):
+    the same fp32 coordinates the benchmark's launch sees."""
+    X, Y = sc.grid(1024, 1024)
+    X, Y = X[5::79, 11::89][:n, :m], Y[5::79, 11::89][:n, :m]
+    return np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+
+
+@pytest.mark.parametrize("mode,alpha", [("hard_sigmoid", 100.0), ("hard_sigmoid", 20.0), ("sigmoid", 30.0), ("hard", 100.0)])
+def test_vjp_raw_geojson_bench_config(mode, alpha):
+    """
+    The workload of bench.py: example.geojson in RAW lon/lat coordinates, orders 0-2 (785 candidates), forward + VJP
+    w.r.t. receivers, object vertices, TX and alpha, on points of the benchmark's own grid.
+
+    1. validity of every (receiver, candidate) bit-identical to the C oracle (hard / hard_sigmoid; sigmoid rtol 1e-5);
+    2. Z and every cotangent ELEMENTWISE against torch autograd over the restated graph (fp32, clean gradients);
+    3. third leg: the same oracle in binary64.  On raw lon/lat coordinates (|y| ~ 50.7, walls ~ 1e-4 long) fp32 leaves
+       ~3 % of a wall length of noise on every parametric coordinate, so the REFERENCE'S OWN fp32 map and gradients are
+       far from their fp64 values at most receivers.  Entries where the fp32 and fp64 oracles agree to 1e-3
+       must meet the elementwise bar outright; the others must be no farther from the fp32 oracle than the fp32 oracle
+       is from fp64 (test_gpu_parity._close).  The excluded counts are printed.
+    """
+    sc = SCENES["geojson"]
+    X, Y = _bench_subgrid(sc)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    Zbar = np.random.default_rng(17).standard_normal(X.shape).astype(np.float32)
+    # 1. validity pattern
+    Zf, v = F.power_fwd(_cfg(mode, max_order=2, grid_cols=X.shape[1]), xys, fixed, grid, alpha=alpha, want_valid=True,
+                        device="cuda")
+    Zc, vc = CO.power_map(xys, fixed, grid, max_order=2, mode=mode, alpha=alpha, want_valid=True)
+    v = v.cpu().numpy()
+    if mode == "sigmoid":
+        np.testing.assert_allclose(v, vc, rtol=1e-5, atol=2.5e-7)
+    else:
+        assert np.array_equal(v, vc), f"{int((v != vc).sum())} of {v.size} validity values differ from the C oracle"
+    assert (vc != 0).sum() > 0
+    # 2. + 3. value and cotangents
+    Zo, go = _oracle_vjp(sc, X, Y, Zbar, mode, alpha)
+    Z64, g64 = _oracle_vjp64(sc, X, Y, Zbar, mode, alpha)
+    out = F.power_value_and_vjp(_cfg(mode, max_order=2, reduce_all=True, grid_cols=X.shape[1]), xys, fixed, grid,
+                                Zbar.reshape(-1), alpha=alpha, device="cuda")
+    out = {k: t.cpu().numpy() for k, t in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
+    report = []
+    for key, okey in (("grid", "grid"), ("fixed", "fixed"), ("objects", "xys"), ("alpha", "alpha")):
+        if key == "alpha" and mode == "hard":
+            assert out["alpha"][0] == 0.0
+            continue
+        got = out[key].reshape(-1).astype(np.float64)
+        w32 = go[okey].numpy().reshape(-1).astype(np.float64)
+        w64 = g64[okey].numpy().reshape(-1).astype(np.float64)
+        scale = max(np.abs(w32).max(), 1e-30)
+        agree = np.abs(w32 - w64) <= 1e-3 * np.abs(w64) + 1e-6 * scale  # the oracle is well conditioned here
+        tol = 1e-4 * np.abs(w32) + 1e-6 * scale
+        bad = (np.abs(got - w32) > tol) & agree
+        assert not bad.any(), (f"{key}_bar: {int(bad.sum())} of {int(agree.sum())} well-conditioned entries miss rtol 1e-4; "
+                               f"worst |diff| {np.abs(got - w32)[bad].max():.3g} at scale {scale:.3g}")
+        n_esc = _close(got, w32, 1e-4, f"{key}_bar (raw lon/lat)", w64, max_escaped=1.0)
+        report.append(f"{key}: {int((~agree).sum())}/{agree.size} ill-conditioned in fp32, {n_esc} accepted via fp64 leg")
+    print(f"[parity] raw geojson {mode} alpha={alpha:g}: " + "; ".join(report))
+
+
+@pytest.mark.parametrize("name", ["basic", "obstacle"])
+@pytest.mark.parametrize("mode,alpha", [("hard", 100.0), ("hard_sigmoid", 20.0), ("hard_sigmoid", 100.0), ("sigmoid", 10.0)])
+def test_transmitters_grid_forward_and_vjp_vs_oracle(name, mode, alpha):
+    """Scene.accumulate_on_transmitters_grid_over_paths (scene.py:1489-1648, the role the reference's own benchmark
+    times, tests/benchmarks/test_scene.py:9-29): validity of every (receiver, TX grid point, candidate), the map and
+    the full VJP (TX grid points, fixed receivers, vertices, alpha) against the oracle, two receivers, three logics."""
+    sc = SCENES[name].update_receivers(rx2=d.Point(xy=[0.8, 0.3]))
+    scg = H.generic_position(sc)
+    X, Y = H.jittered_grid(sc, 18, 20, seed=5)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    for scene, check_objects in ((sc, mode == "hard"), (scg, True)):
+        xys, kinds, phis = scene.packed_objects()
+        fixed = np.stack([p.xy for p in scene.receivers.values()])
+        cfg = _cfg(mode, max_order=2, grid_role="transmitters", grid_cols=X.shape[1])
+        Z, v = F.power_fwd(cfg, xys, fixed, grid, alpha=alpha, want_valid=True, device="cuda")
+        Zc, vc = CO.power_map(xys, fixed, grid, grid_role="transmitters", max_order=2, mode=mode, alpha=alpha,
+                              want_valid=True)
+        if mode == "sigmoid":
+            np.testing.assert_allclose(v.cpu().numpy(), vc, rtol=1e-5, atol=2.5e-7)
+            np.testing.assert_allclose(Z.cpu().numpy(), Zc, rtol=1e-5, atol=1e-6)
+        else:
+            assert np.array_equal(v.cpu().numpy(), vc)
+            np.testing.assert_allclose(Z.cpu().numpy(), Zc, rtol=1e-6, atol=0)
+        Zbar = np.random.default_rng(8).standard_normal(X.shape).astype(np.float32)
+        Zo, go = _oracle_vjp(scene, X, Y, Zbar, mode, alpha, role="transmitters")
+        cache = {}
+
+        def g64(key, scene=scene, cache=cache):
+            def f():
+                if "g" not in cache:
+                    cache["g"] = _oracle_vjp64(scene, X, Y, Zbar, mode, alpha, role="transmitters")[1]
+                return cache["g"][key].numpy()
+            return f
+
+        for use_mask in (False, True):
+            rcfg = _cfg(mode, max_order=2, grid_role="transmitters", grid_cols=X.shape[1], reduce_all=True)
+            if use_mask:
+                out = F.power_value_and_vjp(rcfg, xys, fixed, grid, Zbar.reshape(-1), alpha=alpha, device="cuda")
+            else:
+                out = F.power_bwd(rcfg, xys, fixed, grid, Zbar.reshape(-1), alpha=alpha, device="cuda")
+            out = {k: t.cpu().numpy() for k, t in out.items()}
+            np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
+            _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar (TX grid)", g64("grid"))
+            _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar (receivers)", g64("fixed"), max_escaped=1.0)
+            if check_objects:  # (axis-aligned scenes: structural ties, DESIGN.md "Ties")
+                _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar", g64("xys"), max_escaped=0.25)
+            if mode != "hard":
+                _close(out["alpha"], go["alpha"].numpy().reshape(1), 1e-4, "alpha_bar", g64("alpha"), max_escaped=1.0)
+
+
+def _ris_image_scene():
+    """square_scene + a RIS (examples/plot_ris_power_map.py:37-73 geometry) + one slanted wall, in generic position."""
+    sc = d.Scene.square_scene().add_objects(d.RIS(xys=[[0.5, 0.3], [0.5, 0.7]], phi=float(np.pi / 4)),
+                                            d.Wall(xys=[[0.7, 0.15], [0.9, 0.35]]))
+    return H.generic_position(sc)
+
+
+@pytest.mark.parametrize("mode,alpha", [("hard", 100.0), ("hard_sigmoid", 2.0), ("hard_sigmoid", 50.0), ("sigmoid", 3.0)])
+def test_ris_inside_image_path_vs_oracle(mode, alpha):
+    """RIS objects visited by ImagePath candidates (RIS is a Wall subclass: image_of / intersects / contains are the
+    wall's, the residual is RIS.evaluate_cartesian, geometry.py:698-711): validity, map and VJP including the phi
+    cotangent against the oracle.  Small alpha keeps act(tol - loss) alive for the non-specular RIS residuals."""
+    sc = _ris_image_scene()
+    X, Y = H.jittered_grid(sc, 14, 15, seed=6)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    assert kinds[4] == 1 and phis[4] != 0
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    Z, v = F.power_fwd(_cfg(mode, max_order=2, grid_cols=X.shape[1]), xys, fixed, grid, kinds=kinds, phis=phis,
+                       alpha=alpha, want_valid=True, device="cuda")
+    Zc, vc = CO.power_map(xys, fixed, grid, kinds=kinds, phis=phis, max_order=2, mode=mode, alpha=alpha, want_valid=True)
+    if mode == "hard":
+        assert np.array_equal(v.cpu().numpy(), vc) and np.array_equal(Z.cpu().numpy(), Zc)
+    else:
+        # sinf / cosf of phi: CUDA libm vs glibc may differ in the last bit -> the RIS residual is not bit-pinned
+        np.testing.assert_allclose(v.cpu().numpy(), vc, rtol=2e-5, atol=1e-6)
+        np.testing.assert_allclose(Z.cpu().numpy(), Zc, rtol=2e-5, atol=1e-6)
+    Zbar = np.random.default_rng(9).standard_normal(X.shape).astype(np.float32)
+    Zo, go = _oracle_vjp(sc, X, Y, Zbar, mode, alpha)
+    g64c = {}
+
+    def g64(key):
+        def f():
+            if "g" not in g64c:
+                g64c["g"] = _oracle_vjp64(sc, X, Y, Zbar, mode, alpha)[1]
+            return g64c["g"][key].numpy()
+        return f
+
+    out = F.power_value_and_vjp(_cfg(mode, max_order=2, reduce_all=True, grid_cols=X.shape[1]), xys, fixed, grid,
+                                Zbar.reshape(-1), kinds=kinds, phis=phis, alpha=alpha, device="cuda")
+    out = {k: t.cpu().numpy() for k, t in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=2e-5, atol=1e-6)
+    _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar", g64("grid"))
+    _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar", g64("fixed"), max_escaped=1.0)
+    _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar", g64("xys"), max_escaped=0.25)
+    _close(out["phis"], go["phis"].numpy(), 1e-4, "phis_bar", g64("phis"), max_escaped=1.0)
+    if mode != "hard":
+        _close(out["alpha"], go["alpha"].numpy().reshape(1), 1e-4, "alpha_bar", g64("alpha"), max_escaped=1.0)
+        assert np.abs(out["phis"]).max() > 0, "the RIS angle carries no gradient in this configuration"
+
+
+@pytest.mark.parametrize("mode", ["hard", "hard_sigmoid"])
+def test_non_default_received_power_parameters(mode):
+    """utils.received_power(r_coef=0.7, height=0.25) (utils.py:16-54; Python-float constants folded in double, then
+    cast): hard map bit-exact against the C oracle, smooth map and VJP against the autograd oracle."""
+    sc = H.generic_position(SCENES["obstacle"])
+    X, Y = H.jittered_grid(sc, 16, 18, seed=12)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    kw = dict(r_coef=0.7, height=0.25)
+    cfg = _cfg(mode, max_order=2, grid_cols=X.shape[1], reduce_all=True, **kw)
+    Z = F.power_fwd(cfg, xys, fixed, grid, alpha=40.0, device="cuda")
+    Zc = CO.power_map(xys, fixed, grid, max_order=2, mode=mode, alpha=40.0, reduce_all=True, **kw)
+    if mode == "hard":
+        assert np.array_equal(Z.cpu().numpy(), Zc)
+    else:
+        np.testing.assert_allclose(Z.cpu().numpy(), Zc, rtol=1e-6, atol=0)
+    Zd = CO.power_map(xys, fixed, grid, max_order=2, mode=mode, alpha=40.0, reduce_all=True)
+    assert not np.allclose(Zc, Zd, rtol=1e-3), "the parameters must matter"
+    Zbar = np.random.default_rng(10).standard_normal(X.shape).astype(np.float32)
+    osc = H.oracle_scene_from_product(sc)
+    with R.clean_gradients():
+        Zo, go = R.power_map_and_vjp(osc, X, Y, Zbar, max_order=2, approx=mode != "hard", alpha=40.0,
+                                     function=FN[mode], fun_kwargs=kw)
+    out = F.power_value_and_vjp(cfg, xys, fixed, grid, Zbar.reshape(-1), alpha=40.0, device="cuda")
+    out = {k: t.cpu().numpy() for k, t in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-5, atol=1e-6)
+    _close(out["grid"].reshape(*X.shape, 2), go["grid"].numpy(), 1e-4, "grid_bar")
+    _close(out["fixed"], go["fixed"].numpy(), 1e-4, "fixed_bar")
+    _close(out["objects"], go["xys"].numpy(), 1e-4, "objects_bar")
+    # the Scene API forwards fun_kwargs (scene.py:1909 fun(..., **fun_kwargs))
+    Zs = sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=d.received_power, fun_kwargs=kw, reduce_all=True,
+                                                    max_order=2, approx=mode != "hard", alpha=40.0)
+    assert np.array_equal(Zs.reshape(-1), Z.cpu().numpy())
+
+
+def test_golden_fixture_vjp_on_raw_geojson():
+    """tests/golden/power_fixtures.npz holds the VJP of the raw lon/lat scene in fp32 AND fp64: the CUDA path against
+    the committed fp32 vectors, with the committed fp64 leg deciding which entries are meaningful in fp32."""
+    import os
+
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "power_fixtures.npz"))
+    name = "geojson"
+    X, Y, xys, fixed = g[f"{name}/X"], g[f"{name}/Y"], g[f"{name}/xys"], g[f"{name}/fixed"]
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    out = F.power_bwd(_cfg("hard_sigmoid", max_order=2, reduce_all=True, grid_cols=X.shape[1]), xys, fixed, grid,
+                      g[f"{name}/vjp/Zbar"].reshape(-1), alpha=20.0, device="cuda")
+    out = {k: t.cpu().numpy() for k, t in out.items()}
+    np.testing.assert_allclose(out["Z"].reshape(X.shape), g[f"{name}/vjp/Z"], rtol=1e-5, atol=1e-6)
+    for key, okey in (("grid", "grid"), ("fixed", "fixed"), ("objects", "xys"), ("alpha", "alpha")):
+        _close(out[key].reshape(-1), g[f"{name}/vjp/{okey}_bar"].reshape(-1), 1e-4, f"{key}_bar",
+               g[f"{name}/vjp64/{okey}_bar"].reshape(-1), max_escaped=1.0)
+
+
+# ---- BASELINE config 5: optimisation loop over accumulate_over_paths, candidate-sharded long lists ---------------------
+def _oracle_link_powers(osc, tx, alpha, max_order, approx):
+    """scene.accumulate_over_paths for one transmitter (scene.py:1272-1334) on the oracle: list of per-receiver powers."""
+    logic = R.Logic(approx, alpha, "hard_sigmoid")
+    cands = R.all_path_candidates(osc.n, 0, max_order)
+    return [R._facc(osc, tx, rx, cands, logic, method="image", fun="received_power", fun_kwargs={}, tol=1e-2,
+                    patch=0.0, x0=None, steps=100, lr=0.1, differentiable=True) for rx in osc.receivers.values()]
+
+
+@pytest.mark.parametrize("max_order", [0, 1])
+def test_power_optimize_loop_matches_the_oracle(max_order):
+    """
+    examples/plot_power_optimize.py:63-91,168-229 of the reference, restated on torch: loss(tx) = -min over the two
+    receivers of accumulate_over_paths(received_power)/P0, jax.value_and_grad -> optax.adam(0.01) + zero_nans,
+    alpha = logspace(0, 2, 101) with approximation.  The product side calls Scene.accumulate_over_paths with
+    Point(xy=<tensor requiring grad>) under torch autograd (the CUDA forward + VJP kernels through functional.power_map);
+    the oracle side is the restated graph + autograd (clean gradients == zero_nans on the un == 0 / d == 0 branches).
+    The transmitter trajectories must agree to rtol 1e-3 over 20 iterations.
+    """
+    sc0 = d.Scene.square_scene_with_obstacle().with_receivers(rx_0=d.Point(xy=[0.3, 0.1]), rx_1=d.Point(xy=[0.5, 0.1]))
+    osc = H.oracle_scene_from_product(sc0)
+    alphas = np.logspace(0, 2, 101).astype(np.float32)[:20]
+    start = [0.5, 0.7]
+
+    def run(loss_fn):
+        tx = torch.tensor(start, dtype=torch.float32, requires_grad=True)
+        opt = torch.optim.Adam([tx], lr=0.01)  # optax.adam(0.01): b1 .9, b2 .999, eps 1e-8, bias-corrected
+        traj, losses = [], []
+        for a in alphas:
+            opt.zero_grad()
+            loss = loss_fn(tx, float(a))
+            loss.backward()
+            tx.grad.nan_to_num_(nan=0.0)  # optax.zero_nans()
+            opt.step()
+            traj.append(tx.detach().clone().numpy())
+            losses.append(float(loss))
+        return np.stack(traj), np.asarray(losses)
+
+    def loss_product(tx, alpha):
+        scene = sc0.with_transmitters(tx=d.Point(xy=tx))
+        acc = None
+        for _, _, power in scene.accumulate_over_paths(fun=d.received_power, max_order=max_order, approx=True, alpha=alpha):
+            pw = power / d.P0
+            acc = pw if acc is None else torch.minimum(acc, pw)
+        return -acc.cpu() if acc.device.type != "cpu" else -acc
+
+    def loss_oracle(tx, alpha):
+        with R.clean_gradients():
+            acc = None
+            for power in _oracle_link_powers(osc, tx, alpha, max_order, True):
+                pw = power / R.P0
+                acc = pw if acc is None else torch.minimum(acc, pw)
+            return -acc
+
+    tp, lp = run(loss_product)
+    to, lo = run(loss_oracle)
+    np.testing.assert_allclose(lp, lo, rtol=1e-3, err_msg="loss trajectory")
+    np.testing.assert_allclose(tp, to, rtol=1e-3, err_msg="transmitter trajectory")
+    assert np.abs(tp[-1] - np.asarray(start)).max() > 0.05, "the transmitter did not move"
+
+
+def test_scene_entry_points_are_differentiable_under_autograd():
+    """The analogue of jax.grad over Scene.accumulate_on_receivers_grid_over_paths(reduce_all=True) w.r.t. a wall
+    vertex, the transmitter and alpha, through the Scene API itself, against the direct VJP."""
+    base = H.generic_position(SCENES["obstacle"])
+    X, Y = H.jittered_grid(base, 12, 14, seed=4)
+    w3 = torch.tensor(base.objects[3].xys, requires_grad=True)
+    txt = torch.tensor([0.2, 0.2], requires_grad=True)
+    alpha = torch.tensor(30.0, requires_grad=True)
+    objs = list(base.objects)
+    objs[3] = d.Wall(xys=w3)
+    sc = d.Scene({"tx": d.Point(xy=txt)}, base.receivers, objs)
+    Z = sc.accumulate_on_receivers_grid_over_paths(X, Y, reduce_all=True, max_order=2, approx=True, alpha=alpha)
+    assert isinstance(Z, torch.Tensor) and Z.shape == X.shape and Z.requires_grad
+    Zbar = torch.as_tensor(np.random.default_rng(2).standard_normal(X.shape).astype(np.float32), device=Z.device)
+    (Z * Zbar).sum().backward()
+    xys, _, _ = base.packed_objects()
+    ref = F.power_bwd(_cfg("hard_sigmoid", max_order=2, reduce_all=True, grid_cols=X.shape[1]), xys,
+                      np.array([[0.2, 0.2]], np.float32), np.stack([X, Y], -1).reshape(-1, 2), Zbar.reshape(-1),
+                      alpha=30.0, device="cuda")
+    sc_ = max(float(ref["objects"].abs().max()), 1e-30)
+    assert torch.allclose(w3.grad, ref["objects"][3].cpu(), rtol=1e-3, atol=1e-4 * sc_)
+    assert torch.allclose(txt.grad, ref["fixed"][0].cpu(), rtol=1e-3, atol=1e-4 * float(ref["fixed"].abs().max()))
+    assert torch.allclose(alpha.grad.reshape(1), ref["alpha"].cpu(), rtol=1e-3)
+
+
+@pytest.mark.parametrize("mode", ["hard", "hard_sigmoid"])
+@pytest.mark.parametrize("shards", [2, 3, 8])
+def test_candidate_shards_sum_to_the_unsharded_link(mode, shards):
+    """point-to-point links whose candidate list is sharded over GPUs.  All shards traced one after the
+    other on this GPU: validity flags are disjoint over the shards and OR to the unsharded flags bit for bit; the
+    partial Z and cotangents add up to the unsharded ones (fp32 summation order aside)."""
+    from tests.test_gpu_parity import _random_walls
+
+    sc = _random_walls(60, length=0.15)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    grid = np.stack([p.xy for p in sc.receivers.values()])
+    kw = dict(min_order=0, max_order=3)
+    Zf, vf = F.power_fwd(_cfg(mode, **kw), xys, fixed, grid, alpha=30.0, want_valid=True, device="cuda")
+    full = F.power_value_and_vjp(_cfg(mode, **kw), xys, fixed, grid, None, alpha=30.0, device="cuda")
+    assert float(vf.sum()) > 0
+    vsum = torch.zeros_like(vf)
+    acc = None
+    for s in range(shards):
+        cfg = _cfg(mode, cand_shard=(s, shards), **kw)
+        _, v = F.power_fwd(cfg, xys, fixed, grid, alpha=30.0, want_valid=True, device="cuda")
+        assert float(((v != 0) & (vsum != 0)).sum()) == 0, "two shards traced the same candidate"
+        vsum += v
+        part = F.power_value_and_vjp(cfg, xys, fixed, grid, None, alpha=30.0, device="cuda")
+        acc = part if acc is None else {k: acc[k] + part[k] for k in acc}
+    assert torch.equal(vsum, vf)
+    for k in full:
+        scale = max(float(full[k].abs().max()), 1e-30)
+        assert torch.allclose(acc[k], full[k], rtol=1e-4, atol=1e-5 * scale), k
+    # the single-process form of the multi-GPU entry point (world size 1 = the whole list)
+    from differt2d_b200 import distributed as D
+
+    one = D.sharded_link_power_vjp(_cfg(mode, **kw), xys, fixed, grid, None, alpha=30.0, device="cuda")
+    for k in full:
+        scale = max(float(full[k].abs().max()), 1e-30)
+        assert torch.allclose(one[k], full[k], rtol=1e-4, atol=1e-5 * scale), k
+
+
+def test_row_sharded_entry_point_single_process():
+    """distributed.sharded_power_vjp without a process group (world size 1): defaults to the current CUDA device,
+    slices Zbar along the row axis for [T, n, m] cotangents, equals the unsharded call."""
+    from differt2d_b200 import distributed as D
+
+    sc = d.Scene.basic_scene().update_transmitters(tx2=d.Point(xy=[0.7, 0.6]))
+    X, Y = sc.grid(40, 24)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    Zbar = np.random.default_rng(1).standard_normal((2, *X.shape)).astype(np.float32)
+    cfg = _cfg("hard_sigmoid", max_order=2)
+    out = D.sharded_power_vjp(cfg, xys, fixed, X, Y, Zbar, alpha=40.0)
+    assert out["rows"].tolist() == list(range(24))
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    ref = F.power_value_and_vjp(_cfg("hard_sigmoid", max_order=2, grid_cols=40), xys, fixed, grid,
+                                Zbar.reshape(2, -1), alpha=40.0, device="cuda")
+    assert torch.equal(out["Z"], ref["Z"]) and torch.equal(out["grid"], ref["grid"])
+    for k in ("objects", "fixed", "alpha"):
+        assert torch.allclose(out[k], ref[k], rtol=1e-4, atol=1e-5 * float(ref[k].abs().max()))
+    # rows of another rank's share: band layout of a 2-rank job, evaluated here by hand
+    rows = D.row_tiles_cyclic(24, 2, 1)
+    sub = F.power_value_and_vjp(_cfg("hard_sigmoid", max_order=2, grid_cols=40), xys, fixed,
+                                np.stack([X[rows], Y[rows]], -1).reshape(-1, 2).astype(np.float32),
+                                Zbar[:, rows].reshape(2, -1), alpha=40.0, device="cuda")
+    assert torch.equal(sub["Z"].reshape(2, len(rows), 40), ref["Z"].reshape(2, 24, 40)[:, rows])
+
+
+def test_traced_alpha_not_positive_poisons_the_outputs():
+    """A device-resident (traced) alpha cannot be validated on the host: alpha <= 0 must not return plausible numbers
+    (ADVICE r1): every output is NaN; host scalars are rejected with an error."""
+    sc = SCENES["obstacle"]
+    X, Y = sc.grid(16, 16)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.array([[0.2, 0.2]], np.float32)
+    cfg = _cfg("hard_sigmoid", max_order=1, reduce_all=True, grid_cols=16)
+    bad = torch.tensor(-5.0, device="cuda")
+    Z = F.power_fwd(cfg, xys, fixed, grid, alpha=bad, device="cuda")
+    assert bool(torch.isnan(Z).all())
+    out = F.power_bwd(cfg, xys, fixed, grid, None, alpha=bad, device="cuda")
+    assert all(bool(torch.isnan(t).all()) for t in out.values())
+    ok = F.power_fwd(cfg, xys, fixed, grid, alpha=torch.tensor(5.0, device="cuda"), device="cuda")
+    assert bool(torch.isfinite(ok).all())
+    with pytest.raises(d.D2DError):
+        F.power_fwd(cfg, xys, fixed, grid, alpha=-5.0, device="cuda")
+    with pytest.raises(d.D2DError):
+        F.power_map(torch.as_tensor(xys).cuda(), torch.as_tensor(fixed).cuda(), torch.as_tensor(grid).cuda(), cfg=cfg, alpha=0.0)
+    # hard logic does not use alpha at all
+    assert bool(torch.isfinite(F.power_fwd(_cfg("hard", max_order=1), xys, fixed, grid, alpha=-5.0, device="cuda")).all())
+
+
+def test_host_entry_is_reentrant_across_threads():
+    """d2d_power_host keeps its staging arenas per calling thread (include/differt2d_b200.h): concurrent calls from
+    several threads, different problem sizes, each equal to the single-threaded result."""
+    import threading
+
+    sc = d.Scene.basic_scene()
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    cfgs, refs, grids = [], [], []
+    for n, m in [(40, 32), (64, 48), (24, 80), (512, 520)]:
+        X, Y = sc.grid(m, n)
+        grids.append(np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32))
+        cfgs.append(_cfg("hard_sigmoid", max_order=2, reduce_all=True, grid_cols=m))
+        refs.append(F.power_host(cfgs[-1], xys, fixed, grids[-1], None, alpha=25.0))
+    errs = []
+
+    def work(i):
+        try:
+            for _ in range(3):
+                got = F.power_host(cfgs[i], xys, fixed, grids[i], None, alpha=25.0)
+                assert np.array_equal(got["Z"], refs[i]["Z"]) and np.array_equal(got["grid"], refs[i]["grid"])
+            F.L.lib().d2d_host_release()
+        except Exception as e:  # noqa: BLE001
+            errs.append((i, repr(e)))
+
+    ts = [threading.Thread(target=work, args=(i,)) for i in range(4) for _ in range(2)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    assert not errs, errs

@@ -73,12 +73,14 @@ def test_mode_resolution():
 def test_unsupported_requests_raise():
     sc = d.Scene.square_scene()
     X, Y = sc.grid(4)
-    # an arbitrary callable selects the generic escape hatch (paths materialised on the GPU, fun on PathBatch)
-    sc._config("receivers", lambda *a: 0.0, (), None, False, d.ImagePath, None, 0, 1, None, None, {})
-    assert sc._generic
+    # an arbitrary callable selects the generic escape hatch (paths materialised on the GPU, fun on batched arguments);
+    # the flag is RETURNED: no per-call state is kept on the Scene
+    assert sc._config("receivers", lambda *a: 0.0, (), None, False, d.ImagePath, None, 0, 1, None, None, {})[2] is True
+    assert sc._config("receivers", d.received_power, (), None, False, d.ImagePath, None, 0, 1, None, None, {})[2] is False
+    assert not hasattr(sc, "_generic")
     with pytest.raises(NotImplementedError):
         sc._config("receivers", "not a function", (), None, False, d.ImagePath, None, 0, 1, None, None, {})
-    cfg3, _ = sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"many": 3}, 0, 1, None, None, {})
+    cfg3, _, _ = sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"many": 3}, 0, 1, None, None, {})
     assert cfg3.many == 3 and sc._x0(cfg3, 7, None).shape == (5, 3, 1)  # optimize.py:142-182 restarts
     with pytest.raises(NotImplementedError):
         sc._config("receivers", d.received_power, (), None, False, d.MinPath, {"optimizer": object()}, 0, 1, None, None, {})
@@ -87,7 +89,7 @@ def test_unsupported_requests_raise():
     with pytest.raises(TypeError):
         sc.add_objects(d.Vertex(xy=[0.3, 0.3]))._config("receivers", d.received_power, (), None, False, d.ImagePath,
                                                         None, 0, 1, None, None, {})
-    cfg, alpha = sc._config("receivers", d.received_power, (), {"r_coef": 0.3, "height": 0.0}, True, d.FermatPath,
+    cfg, alpha, _ = sc._config("receivers", d.received_power, (), {"r_coef": 0.3, "height": 0.0}, True, d.FermatPath,
                             {"steps": 7}, 0, 1, 2, None, {"approx": True, "alpha": 12.0, "tol": 0.5})
     assert (cfg.min_order, cfg.max_order, cfg.steps, cfg.r_coef, cfg.height, cfg.mode, cfg.tol) == \
            (2, 2, 7, 0.3, 0.0, "hard_sigmoid", 0.5) and alpha == 12.0
@@ -156,6 +158,17 @@ def test_cyclic_row_bands_partition_the_grid():
                 assert all((int(i) // 8) % w == r for i in p)                    # whole 8-row bands, round robin
             if n % (8 * w) == 0:
                 assert len({len(p) for p in parts}) == 1                         # equal shares
+
+
+@pytest.mark.parametrize("G,slices,shards", [(1000, 1, 2), (124_500_500, 7, 8), (129, 3, 4), (0, 1, 2), (249_500, 37, 3)])
+def test_candidate_shards_partition_the_list(G, slices, shards):
+    """SURVEY §8e, point-to-point links: the chunks of 128 candidates are dealt to the candidate shards (one per GPU)
+    so that every chunk is traced exactly once, and long lists are split evenly (csrc/d2d_driver.cuh)."""
+    per = [D.candidate_chunks_of_shard(G, slices, s, shards) for s in range(shards)]
+    allq = np.concatenate(per)
+    assert sorted(allq.tolist()) == list(range((G + 127) // 128))
+    if G > 128 * slices * shards * 8:
+        assert max(len(q) for q in per) - min(len(q) for q in per) <= slices
 
 
 def test_pack_unpack_roundtrip():
