@@ -516,7 +516,9 @@ def parity_spotcheck(job, Z, gbar) -> dict:
     gg = gh[np.ix_(ri, ci)].reshape(-1, 2).astype(np.float64)
     w32, w64 = a32["grid"], a64["grid"]
     scale = max(np.abs(w32).max(), 1e-30)
-    agree = np.abs(w32 - w64) <= 1e-3 * np.abs(w64) + 1e-6 * scale   # well conditioned in fp32
+    # well conditioned in fp32: the oracle's own fp32 evaluation is within 1e-5 of its fp64 value (an order below the
+    # bar, so that a second fp32 evaluation of the same size of error — the kernel's — can be held to rtol 1e-4)
+    agree = np.abs(w32 - w64) <= 1e-5 * np.abs(w64) + 1e-7 * scale
     err = np.abs(gg - w32) / (np.abs(w32) + 1e-6 * scale)
     noise = np.abs(w32 - w64)
     within_noise = np.abs(gg - w32) <= 1e-4 * np.abs(w32) + 1e-6 * scale + 4.0 * noise + 4.0 * np.percentile(noise, 90)
@@ -527,8 +529,9 @@ def parity_spotcheck(job, Z, gbar) -> dict:
                          "well_conditioned_entries": int(agree.sum()), "max_rel_on_those": g_rel,
                          "all_within_oracle_fp32_noise": bool(within_noise.all()),
                          "vs": "dual-number VJP of oracle/d2d_oracle_ad.cpp in fp32; 'well conditioned' = its fp32 and fp64 "
-                               "evaluations agree to 1e-3 (raw lon/lat coordinates put fp32 noise on the reference's own "
-                               "cotangents, tests/test_gpu_parity_round2.py)"},
+                               "evaluations agree to 1e-5 (raw lon/lat coordinates put fp32 noise on the reference's own "
+                               "cotangents, tests/test_gpu_parity_round2.py); everywhere: |kernel - oracle32| <= rtol 1e-4 "
+                               "+ 4 |oracle32 - oracle64| + 4 P90"},
             "ok": bool(z_rel <= 1e-5 and (g_rel is None or g_rel <= 1e-4) and within_noise.all())}
 
 
@@ -544,6 +547,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the dense leg, the strong-scaling leg and the spot check")
+    ap.add_argument("--only-dense", action="store_true", help="profiling aid: run the un-prunable leg alone and print it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -569,6 +573,11 @@ def main() -> None:
     barrier = D.barrier if dist is not None else None
     if args.workload == "p2p500":
         bench_p2p500(args, torch, L, F, D, dev, world, rank, dist)
+        return
+
+    if args.only_dense:
+        flush = torch.empty(FLUSH_BYTES, dtype=torch.uint8, device=dev)
+        _emit(dense_leg(torch, L, F, dev, flush, min(args.steps, 10), 72.5))
         return
 
     sc = load_scene(args.coords)

@@ -11,6 +11,7 @@
 // reduced warp (shuffle) -> CTA (shared-memory atomics) -> device (global fp32 atomics); the
 // multi-GPU all-reduce of these few KB happens in the host layer (differt2d_b200/distributed.py).
 #include "d2d_driver.cuh"
+#include "d2d_image_bwd.cuh"
 #include "d2d_launch.h"
 #include "d2d_solver.cuh"
 #include "d2d_solver_adj.cuh"
@@ -327,24 +328,31 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
             int occ_j = -1;
             float4 occ_bar = make_float4(0.f, 0.f, 0.f, 0.f);
             if (tile.active) {
-                // light re-trace first (same code as the forward kernel); the reverse sweep is out of line
-                // and only runs for the few paths whose validity is non-zero
-                float2 X[K + 2];
-                float valid = 0.0f;
                 if constexpr (METHOD == D2D_METHOD_IMAGE) {
-                    float onx;
+                    // ONE tracked re-trace (the forward kernel's arithmetic, plus the arg-min / arg-max bookkeeping of
+                    // the reverse sweep), then the sweep from the live registers (d2d_image_bwd.cuh)
+                    ImageTrace<K> tr;
                     const float2 ap = TXGRID ? image_apex<K>(T, cd, tx) : apex;
-                    if (image_path_on<MODE, K>(T, cd, tx, rx, ap, alpha, X, onx))
-                        valid = validity_from_onx<MODE, K, true>(T, p, alpha, cd, X, 0.0f, onx, &sh.hint[threadIdx.x >> 5]);
+                    if (trace_image_tracked<MODE, K>(T, p, alpha, cd, tx, rx, ap, tr, &sh.hint[threadIdx.x >> 5])) {
+                        A.acc = A.acc + tr.valid * tr.val;
+                        if (zbar != 0.0f) {
+                            has = true;
+                            image_reverse<MODE, K>(T, p, alpha, cd, tr, zbar, txb, rxb, ab, oa, occ_j, occ_bar);
+                        }
+                    }
                 } else {
+                    // light re-trace first (same code as the forward kernel); the reverse sweep through the Adam scan
+                    // is out of line and only runs for the paths whose validity is non-zero
+                    float2 X[K + 2];
                     float loss;
                     construct_path<METHOD, K>(T, p, cd, tx, rx, col, X, loss);
-                    valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(T, p, alpha, cd, X, loss, &sh.hint[threadIdx.x >> 5]);
-                }
-                if (valid != 0.0f) {
-                    const float c = path_vjp<MODE, METHOD, K>(T, p, alpha, cd, tx, rx, col, zbar, has, txb, rxb, ab,
-                                                              oa, occ_j, occ_bar);
-                    A.acc = A.acc + c;
+                    const float valid = validity<MODE, K, (METHOD != D2D_METHOD_MINPATH) || K == 0>(
+                        T, p, alpha, cd, X, loss, &sh.hint[threadIdx.x >> 5]);
+                    if (valid != 0.0f) {
+                        const float c = path_vjp<MODE, METHOD, K>(T, p, alpha, cd, tx, rx, col, zbar, has, txb, rxb, ab,
+                                                                  oa, occ_j, occ_bar);
+                        A.acc = A.acc + c;
+                    }
                 }
             }
             if (has) {
@@ -353,11 +361,24 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
                 A.grid_bar.x += gb.x; A.grid_bar.y += gb.y;
                 A.fixed_bar.x += fb.x; A.fixed_bar.y += fb.y;
                 A.alpha_bar += ab;
-                if (occ_j >= 0 && s_obj) {
-                    atomicAdd(&s_obj[4 * occ_j + 0], occ_bar.x);
-                    atomicAdd(&s_obj[4 * occ_j + 1], occ_bar.y);
-                    atomicAdd(&s_obj[4 * occ_j + 2], occ_bar.z);
-                    atomicAdd(&s_obj[4 * occ_j + 3], occ_bar.w);
+            }
+            if (s_obj) {
+                // occluders' vertex cotangents: the lanes of a warp mostly share their arg-max occluder (neighbouring
+                // receivers, same candidate), and 32 shared-memory atomics on one address serialise: one warp reduction
+                // per DISTINCT occluder instead (uniform over the warp: the visit is)
+                unsigned pend = __ballot_sync(0xffffffffu, has && occ_j >= 0);
+                while (pend) {
+                    const int j0 = __shfl_sync(0xffffffffu, occ_j, __ffs(pend) - 1);
+                    const bool mine = has && occ_j == j0;
+                    float4 v = mine ? occ_bar : make_float4(0.f, 0.f, 0.f, 0.f);
+                    v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
+                    if ((threadIdx.x & 31) == 0) {
+                        atomicAdd(&s_obj[4 * j0 + 0], v.x);
+                        atomicAdd(&s_obj[4 * j0 + 1], v.y);
+                        atomicAdd(&s_obj[4 * j0 + 2], v.z);
+                        atomicAdd(&s_obj[4 * j0 + 3], v.w);
+                    }
+                    pend &= ~__ballot_sync(0xffffffffu, mine);
                 }
             }
             if (K > 0 && s_obj && __any_sync(0xffffffffu, has)) {
@@ -419,8 +440,8 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
         }
         return;
     }
-    if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
-        if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
+    if constexpr (METHOD == D2D_METHOD_IMAGE) {
+        if (p.macro) macro_prologue<MODE, TXGRID>(T, p, tile, sh, alpha);
     }
     if (p.mask && mask_bitmap_fits(p)) mask_prologue(p, sh);
     const float2 g = active ? reinterpret_cast<const float2*>(p.grid)[r] : make_float2(0.f, 0.f);
@@ -524,7 +545,7 @@ static int launch_bwd_one(const KParams& p, const float* Zbar, const BwdOut& out
     }
     // without an activity mask the backward re-runs the culls: clusters + macro-tile cull as in the forward kernel
     KParams q = p;
-    q.macro = (host_macro_ok(p) && !p.mask && METHOD == D2D_METHOD_IMAGE && !TXGRID) ? 1 : 0;
+    q.macro = (host_macro_ok(p) && !p.mask && METHOD == D2D_METHOD_IMAGE) ? 1 : 0;  // both grid roles
     const cudaError_t e = launch_tiles(kern, q, q.macro != 0, smem, stream, q, Zbar, out);
     return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }

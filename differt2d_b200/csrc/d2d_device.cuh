@@ -29,6 +29,14 @@
 
 namespace d2d {
 
+// Optional census of the culls and of the trace (diagnostic builds only: python -m differt2d_b200.build --debug-counters)
+#ifdef D2D_DEBUG_COUNTERS
+__device__ unsigned long long d2d_dbg[32];
+#define D2D_COUNT(i) atomicAdd(&d2d_dbg[i], 1ULL)
+#else
+#define D2D_COUNT(i) ((void)0)
+#endif
+
 constexpr float kEps32 = 1.1920928955078125e-07f;  // geometry.py:200
 constexpr float kTolSeg = 0.005f;                  // geometry.py:89
 constexpr float kHiSeg = 1.0f + 0.005f;            // geometry.py:169  fl(1.0 + tol)
@@ -156,6 +164,17 @@ __device__ __forceinline__ bool act_is_zero(float x, float alpha) {
     const float z = alpha * x;
     if (z > -87.0f) return false;  // expf(87) is finite: 1/(1+e) > 0
     return act<MODE>(x, alpha) == 0.0f;
+}
+
+// act(x) == 1 for sure?  (`intersects` is then exactly true / 1.0: the path is dead.)  Conservative on purpose: a
+// "no" only means that the fold goes on and the exact validity is formed at the end, so the results do not depend on
+// it — while evaluating the activation itself on every update of the running maximum cost an expf and an IEEE
+// division in the sigmoid kernels (the un-prunable regime spends 70 % of its time in this fold).
+template <int MODE>
+__device__ __forceinline__ bool act_is_one(float x, float alpha) {
+    const float z = alpha * x;
+    if (MODE == D2D_MODE_SIGMOID) return z >= 18.0f;  // expf(-18) < 2^-25: 1 + e rounds to 1 and 1 / 1 == 1
+    return z + 3.0f >= 6.0f;                          // relu6 saturates exactly
 }
 
 // d/dz of f at z = alpha*x (the VJP rules of jnp.minimum/maximum give 1/2 at the kinks)

@@ -55,13 +55,6 @@ constexpr int kMacroTilesX = 2;    // macro tile = 2 x 4 tiles = 32 x 32 grid po
 constexpr int kMacroTilesY = 4;
 constexpr int kMacroWords = 512;   // survivor bitmap: up to 16384 (fixed point, candidate) pairs, else no macro stage
 
-// Optional census of the cull (diagnostic builds only: python -m differt2d_b200.build --debug-counters)
-#ifdef D2D_DEBUG_COUNTERS
-__device__ unsigned long long d2d_dbg[32];
-#define D2D_COUNT(i) atomicAdd(&d2d_dbg[i], 1ULL)
-#else
-#define D2D_COUNT(i) ((void)0)
-#endif
 
 struct Tile {
     long long r;      // grid-point index of this thread (row-major), valid when `active`
@@ -71,6 +64,7 @@ struct Tile {
     float4 wbox;      // same over this thread's warp (inverted / infinite when the warp has no active point)
     float scale;      // max |coordinate| over tile, fixed points and objects (for error bounds)
     float scale_x, scale_y;  // the same per component (lon/lat scenes: |x| ~ 5, |y| ~ 50 — the fp32 lattice differs 8x)
+    float diam;       // extent of the bounding box of tile (macro tile), fixed points and objects: bounds every |P1 - X|
 };
 
 struct DriverShared {
@@ -192,18 +186,25 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     float sx = fmaxf(fabsf(xmin), fabsf(xmax)), sy = fmaxf(fabsf(ymin), fabsf(ymax));
     if (!(sx < CUDART_INF_F)) sx = 0.0f;  // empty tile
     if (!(sy < CUDART_INF_F)) sy = 0.0f;
+    float ex0 = xmin, ex1 = xmax, ey0 = ymin, ey1 = ymax;  // extent of everything in play (inverted for an empty tile)
     for (int j = 0; j < p.N; ++j) {    // uniform, N is small next to the candidate count
         const float4 w = T.w0[j];
         sx = fmaxf(sx, fmaxf(fabsf(w.x), fabsf(w.x + w.z)));
         sy = fmaxf(sy, fmaxf(fabsf(w.y), fabsf(w.y + w.w)));
+        ex0 = fminf(ex0, fminf(w.x, w.x + w.z)); ex1 = fmaxf(ex1, fmaxf(w.x, w.x + w.z));
+        ey0 = fminf(ey0, fminf(w.y, w.y + w.w)); ey1 = fmaxf(ey1, fmaxf(w.y, w.y + w.w));
     }
     for (int f = 0; f < p.T; ++f) {
-        sx = fmaxf(sx, fabsf(p.fixed[2 * f]));
-        sy = fmaxf(sy, fabsf(p.fixed[2 * f + 1]));
+        const float fxx = p.fixed[2 * f], fyy = p.fixed[2 * f + 1];
+        sx = fmaxf(sx, fabsf(fxx));
+        sy = fmaxf(sy, fabsf(fyy));
+        ex0 = fminf(ex0, fxx); ex1 = fmaxf(ex1, fxx);
+        ey0 = fminf(ey0, fyy); ey1 = fmaxf(ey1, fyy);
     }
     t.scale_x = sx;
     t.scale_y = sy;
     t.scale = fmaxf(sx, sy);
+    t.diam = (ex1 >= ex0 && ey1 >= ey0) ? ((ex1 - ex0) + (ey1 - ey0)) * 1.000001f : 0.0f;
     __syncthreads();
     return t;
 }
@@ -382,6 +383,116 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
     return true;
 }
 
+// The same question for a TRANSMITTERS grid (scene.py:1489-1648): the tile holds transmitter positions, `rx` is the fixed
+// receiver.  The per-thread evaluation mirrors ITS transmitter through the candidate, I_0 = tx, I_{i+1} = image(I_i, c_i),
+// and back-projects from the receiver: X_{K+1} = rx, X_{i+1} = line(X_{i+2}, I_{i+1}) ^ wall c_i, i = K-1 ... 0.
+// In exact arithmetic X_{i+1} is also the intersection of wall c_i with the line from I_{i+1}(tx) to the receiver
+// UNFOLDED back through the later walls, R_i = image(... image(rx, c_{K-1}) ..., c_{i+1}) (R_{K-1} = rx): a fixed centre
+// and an apex that is an AFFINE function of tx.  The parametric coordinate s_i is therefore a linear-fractional
+// function of tx for every interaction, and over the tile's box its extrema are at the images of the four corners as
+// long as u.n keeps its sign there.  Only rule (1) is applied (s-range misses [xz, 1 - xz] by more than the error
+// bound), interaction by interaction in the THREAD'S order, so that the error recursion of the thread's chain is
+// available when a stage needs it:
+//     E_{i+1} <= 1.5 L_i (E_{i+2} + EI_{i+1}) + own_i,   E_{K+1} = 0,   L_i = (1 + |g|)(1 + |u| / |u.n|)
+// with EI_m the rounding of an m-fold image (one lattice rounding per mirror plus relative terms) and own_i the
+// rounding of one back-projection (lattice + relative terms, as in tile_may_be_valid; the thread's |P1 - X| is bounded
+// by the scene's extent `diam`, its |g||u| and |u| by this frame's, the ratio |u| / |u.n| is the same in both frames).
+// This evaluation carries the relative terms and the rounding of ITS images (corner images and R_i).
+template <int K>
+__device__ __forceinline__ bool tile_may_be_valid_tx(const SceneTab& T, const int (&c)[K > 0 ? K : 1], const float2 rx,
+                                                     const float4 bbox, const float scale_x, const float scale_y,
+                                                     const float diam, const float xz) {
+    constexpr int KK = K > 0 ? K : 1;
+    if (!(xz > -CUDART_INF_F)) return true;
+    const float eps = 5.9604645e-8f;
+    float2 R[KK];
+    R[K - 1] = rx;
+#pragma unroll
+    for (int i = K - 2; i >= 0; --i) R[i] = mirror(R[i + 1], T.w0[c[i + 1]], T.w1[c[i + 1]]);
+    float2 Ic[4][KK];  // Ic[q][i]: corner q mirrored through c[0 .. i]
+    float simx = scale_x, simy = scale_y;  // largest image coordinates (the lattice the images are rounded onto)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        float2 pt = make_float2((q & 1) ? bbox.z : bbox.x, (q & 2) ? bbox.w : bbox.y);
+#pragma unroll
+        for (int i = 0; i < K; ++i) {
+            pt = mirror(pt, T.w0[c[i]], T.w1[c[i]]);
+            Ic[q][i] = pt;
+            simx = fmaxf(simx, fabsf(pt.x)); simy = fmaxf(simy, fabsf(pt.y));
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < K; ++i) { simx = fmaxf(simx, fabsf(R[i].x)); simy = fmaxf(simy, fabsf(R[i].y)); }
+    // rounding of ONE mirror (p - 2 ((p - P1).n) n with |p - P1| <= (2 K + 1) diam): lattice + relative terms
+    const float e1 = 1.5f * eps * pow2_floor(fmaxf(simx, simy)) + 16.0f * eps * (2.0f * K + 1.0f) * diam;
+    float Enext = 0.0f;
+#pragma unroll
+    for (int i = K - 1; i >= 0; --i) {
+        const int j = c[i];
+        const float4 w0 = T.w0[j];
+        const float4 w1 = T.w1[j];
+        const int kind = T.kind[j];
+        if (kind == D2D_KIND_VERTEX) continue;            // X = previous point, always on the object
+        if (w0.z == 0.0f && w0.w == 0.0f) continue;        // zero-length object: n = 0, X = previous point, s = 0
+        const float EI = (float)(i + 1) * e1;              // the thread's (and this evaluation's) image of level i + 1
+        const float ER = (float)(K - 1 - i) * e1;          // this evaluation's unfolded receiver
+        float smin = CUDART_INF_F, smax = -CUDART_INF_F, gabs = 0.f;
+        float unmin = CUDART_INF_F, U1 = 0.f, V1 = 0.f, uxm = 0.f, uym = 0.f, u2m = 0.f;
+        int pos = 0, neg = 0;
+        const float rtt = rcp_approx(w1.z);
+        const float2 pc = R[i];
+#pragma unroll 1
+        for (int q = 0; q < 4; ++q) {
+            const float2 A = q == 0 ? Ic[0][i] : (q == 1 ? Ic[1][i] : (q == 2 ? Ic[2][i] : Ic[3][i]));
+            const float ux = pc.x - A.x, uy = pc.y - A.y;
+            const float vx = w0.x - pc.x, vy = w0.y - pc.y;
+            const float un = fmaf(ux, w1.x, uy * w1.y);
+            const float vn = fmaf(vx, w1.x, vy * w1.y);
+            pos += un > 0.f;
+            neg += un < 0.f;
+            const float g = vn * rcp_approx(un);
+            const float Dx = fmaf(g, ux, -vx), Dy = fmaf(g, uy, -vy);  // X - P1 in relative form
+            const float sq = fmaf(w0.z, Dx, w0.w * Dy) * rtt;
+            smin = fminf(smin, sq); smax = fmaxf(smax, sq);
+            gabs = fmaxf(gabs, fabsf(g));
+            unmin = fminf(unmin, fabsf(un));
+            U1 = fmaxf(U1, fabsf(ux) + fabsf(uy));
+            V1 = fmaxf(V1, fabsf(vx) + fabsf(vy));
+            uxm = fmaxf(uxm, fabsf(ux)); uym = fmaxf(uym, fabsf(uy));
+            u2m = fmaxf(u2m, fmaf(ux, ux, uy * uy));
+        }
+        u2m = sqrt_approx(u2m) * 1.000001f;
+        if (!(pos == 4 || neg == 4)) return true;                          // u.n may vanish inside the tile
+        if (!(smin == smin) || !(smax == smax) || !(gabs == gabs)) return true;
+        if (!(unmin > 64.0f * eps * U1 + 4.0f * (EI + ER + Enext))) return true;  // u.n not reliably away from zero
+        gabs *= 1.000001f;
+        const float run = rcp_approx(unmin) * 1.000001f;
+        const float lip = (1.0f + gabs) * (1.0f + u2m * run);
+        const float gu1 = gabs * u2m, gu5 = 5.0f * gu1;
+        // the thread's back-projection: |v|_1 <= 2 diam
+        const float ampT = 4.4f * (2.0f * diam + gabs * U1) * run;
+        const float relTx = eps * (0.8f * gu5 + 4.0f * gabs * uxm + ampT * uxm + 4.0f * diam);
+        const float relTy = eps * (0.8f * gu5 + 4.0f * gabs * uym + ampT * uym + 4.0f * diam);
+        const float devT = 1.5f * lip * (Enext + EI);
+        const float dTx = eps * pow2_floor(scale_x + gu1) + relTx + devT;
+        const float dTy = eps * pow2_floor(scale_y + gu1) + relTy + devT;
+        // this evaluation: relative terms with ITS v, and the rounding of its two images
+        const float ampC = 4.4f * (V1 + gabs * U1) * run;
+        const float relCx = eps * (0.8f * gu5 + 4.0f * gabs * uxm + ampC * uxm + 2.0f * V1);
+        const float relCy = eps * (0.8f * gu5 + 4.0f * gabs * uym + ampC * uym + 2.0f * V1);
+        const float devC = 1.5f * lip * (EI + ER);
+        const float smag = fmaxf(fabsf(smin), fabsf(smax));
+        const float ds = (fabsf(w0.z) * (dTx + relCx + devC) + fabsf(w0.w) * (dTy + relCy + devC)) * (rtt * 1.000001f) +
+                         16.0f * eps * smag;
+        const float tol = 2.0f * (1.25f * ds + 1e-6f);  // (x 2: this bound has had less mileage than the receivers-grid one)
+        if (!(tol < CUDART_INF_F)) return true;
+        if (smax < xz - tol || smin > 1.0f - xz + tol) { D2D_COUNT(i == K - 1 ? 1 : 2); return false; }  // rule (1)
+        Enext = fmaxf(dTx, dTy) * 1.25f;  // the thread's X_{i+1}
+    }
+    D2D_COUNT(6);
+    return true;
+}
+
 // Warp-level refinement of rule (1) for the LAST interaction: the s-range over the warp's own bounding box
 // (a sub-box of the tile's), evaluated exactly like the tile-level test at its corners; `tol` is the tile-level
 // error bound (every quantity it is built from is a maximum / minimum over the whole tile, and the tile-level
@@ -425,7 +536,8 @@ template <int K>
 __device__ __forceinline__ CandTest test_candidate_inline(const SceneTab& T, const int m, const long long idx,
                                                           const float2 fx, const bool apex_wanted, const bool cull,
                                                           const float4 box, const float scale, const float scale_x,
-                                                          const float scale_y, const float xz, const float loss_dead) {
+                                                          const float scale_y, const float xz, const float loss_dead,
+                                                          const bool txgrid = false, const float diam = 0.0f) {
     constexpr int KK = K > 0 ? K : 1;
     CandTest o;
     o.apex = fx;
@@ -463,7 +575,12 @@ __device__ __forceinline__ CandTest test_candidate_inline(const SceneTab& T, con
     }
     o.c01 = c[0] | ((K > 1 ? c[K > 1 ? 1 : 0] : 0) << 16);
     o.c23 = (K > 2 ? c[K > 2 ? 2 : 0] : 0) | ((K > 3 ? c[K > 3 ? 3 : 0] : 0) << 16);
-    if (apex_wanted) {
+    if (txgrid) {  // transmitters grid: the images depend on the grid point; fx is the fixed RECEIVER
+        if (cull) {
+            D2D_COUNT(0);
+            if constexpr (K > 0) o.keep = tile_may_be_valid_tx<K>(T, c, fx, box, scale_x, scale_y, diam, xz);
+        }
+    } else if (apex_wanted) {
         float2 I[K + 1];
         I[0] = fx;
 #pragma unroll
@@ -483,9 +600,11 @@ template <int K>
 __device__ __noinline__ CandTest test_candidate(unsigned char* smem, const int N, const int m, const long long idx,
                                                 const float2 fx, const bool apex_wanted, const bool cull,
                                                 const float4 box, const float scale, const float scale_x,
-                                                const float scale_y, const float xz, const float loss_dead) {
+                                                const float scale_y, const float xz, const float loss_dead,
+                                                const bool txgrid, const float diam) {
     const SceneTab T = carve_tab(smem, N);
-    return test_candidate_inline<K>(T, m, idx, fx, apex_wanted, cull, box, scale, scale_x, scale_y, xz, loss_dead);
+    return test_candidate_inline<K>(T, m, idx, fx, apex_wanted, cull, box, scale, scale_x, scale_y, xz, loss_dead,
+                                    txgrid, diam);
 }
 
 // number of candidates of order K over m visitable objects
@@ -525,7 +644,7 @@ __device__ __forceinline__ void bitmap_prefix(DriverShared& sh, const int nwords
 // cooperatively and pushed into every CTA's shared memory; must be called by every thread of every CTA, once, after
 // make_tile().  Word wd of the bitmap is the ballot of one warp over the pairs 32 wd ... 32 wd + 31, pair b = fixed point
 // b / C_total, candidate column b % C_total (orders ascending, list order inside an order).
-template <int MODE>
+template <int MODE, bool TXGRID = false>
 __device__ __forceinline__ void macro_prologue(const SceneTab& T, const KParams& p, const Tile& tile, DriverShared& sh,
                                                const float alpha) {
     cg::cluster_group cl = cg::this_cluster();
@@ -553,10 +672,10 @@ __device__ __forceinline__ void macro_prologue(const SceneTab& T, const KParams&
             D2D_COUNT(20);
             const float ld = p.tol - xz;
             switch (ord) {
-                case 1: k = test_candidate<1>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
-                case 2: k = test_candidate<2>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
-                case 3: k = test_candidate<3>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
-                case 4: k = test_candidate<4>(smem_tab, p.N, m, col, fx, true, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld).keep; break;
+                case 1: k = test_candidate<1>(smem_tab, p.N, m, col, fx, !TXGRID, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld, TXGRID, tile.diam).keep; break;
+                case 2: k = test_candidate<2>(smem_tab, p.N, m, col, fx, !TXGRID, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld, TXGRID, tile.diam).keep; break;
+                case 3: k = test_candidate<3>(smem_tab, p.N, m, col, fx, !TXGRID, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld, TXGRID, tile.diam).keep; break;
+                case 4: k = test_candidate<4>(smem_tab, p.N, m, col, fx, !TXGRID, true, tile.mbox, tile.scale, tile.scale_x, tile.scale_y, xz, ld, TXGRID, tile.diam).keep; break;
                 default: k = true; break;  // order 0: line of sight, never culled
             }
             if (k) D2D_COUNT(21);
@@ -608,7 +727,8 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
     }
     constexpr int KK = K > 0 ? K : 1;
     constexpr bool kApex = (METHOD == D2D_METHOD_IMAGE) && !TXGRID;
-    const bool cull = kApex && p.cull && !mread;
+    constexpr bool kTxCull = (METHOD == D2D_METHOD_IMAGE) && TXGRID;  // transmitters grid: tile_may_be_valid_tx
+    const bool cull = (kApex || kTxCull) && p.cull && !mread;
     const long long wpw = p.mask_wpw;
     const float xz = x_zero<MODE>(alpha);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -631,7 +751,7 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
         }
         if (pre)
             ct = test_candidate_inline<K>(T, m, idx, fx, kApex, cull, tile.bbox, tile.scale, tile.scale_x, tile.scale_y,
-                                          xz, p.tol - xz);
+                                          xz, p.tol - xz, kTxCull, tile.diam);
         const bool keep = ct.keep;
         // ordered compaction: per-warp segments keep list order
         const unsigned ballot = __ballot_sync(0xffffffffu, keep);
@@ -662,7 +782,7 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
                     wk = (mread[warp * wpw + (col >> 5)] >> (col & 31)) & 1u;
                 }
                 todo = __ballot_sync(0xffffffffu, wk);
-            } else if (cull) {  // warp-level refinement: lane q tests survivor q0 + q against this warp's box
+            } else if (cull && kApex) {  // warp-level refinement: lane q tests survivor q0 + q against this warp's box
                 bool wk = false;
                 if (lane < nq && tile.wbox.x <= tile.wbox.z) {  // (a warp without active points skips everything)
                     const int sl = myslot;

@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(con
             for (int t = 0; t < (p.reduce_all ? 1 : p.T); ++t) Z[(long long)t * p.R + tile.r] = CUDART_NAN_F;
         return;
     }
-    if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
-        if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
+    if constexpr (METHOD == D2D_METHOD_IMAGE) {
+        if (p.macro) macro_prologue<MODE, TXGRID>(T, p, tile, sh, alpha);
     }
     const float2 g = tile.active ? reinterpret_cast<const float2*>(p.grid)[tile.r] : make_float2(0.f, 0.f);
     float zsum = 0.0f;
@@ -118,7 +118,7 @@ static int launch_one(const KParams& p, float* Z, float* valid_out, cudaStream_t
     }
     // thread-block clusters (macro-tile cull through distributed shared memory) where there is something to cull
     KParams q = p;
-    q.macro = (host_macro_ok(p) && METHOD == D2D_METHOD_IMAGE && !TXGRID) ? 1 : 0;
+    q.macro = (host_macro_ok(p) && METHOD == D2D_METHOD_IMAGE) ? 1 : 0;  // both grid roles
     const cudaError_t e = launch_tiles(kern, q, q.macro != 0, smem, stream, q, Z, valid_out);
     return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }

@@ -76,8 +76,8 @@ __global__ void __launch_bounds__(kBlock) paths_kernel(const KParams p, const Pa
     build_tab(T, p, &sh.count);
     const Tile tile = make_tile(p, T, sh);
     const float alpha = p.alpha_dev ? *p.alpha_dev : p.alpha;
-    if constexpr (METHOD == D2D_METHOD_IMAGE && !TXGRID) {
-        if (p.macro) macro_prologue<MODE>(T, p, tile, sh, alpha);
+    if constexpr (METHOD == D2D_METHOD_IMAGE) {
+        if (p.macro) macro_prologue<MODE, TXGRID>(T, p, tile, sh, alpha);
     }
     const float2 g = tile.active ? reinterpret_cast<const float2*>(p.grid)[tile.r] : make_float2(0.f, 0.f);
     int buf = 0;
@@ -107,7 +107,7 @@ static int launch_paths_one(const KParams& p, const PathsOut& out, cudaStream_t 
         if (e != cudaSuccess) return (int)e;
     }
     KParams q = p;
-    q.macro = (host_macro_ok(p) && METHOD == D2D_METHOD_IMAGE && !TXGRID) ? 1 : 0;
+    q.macro = (host_macro_ok(p) && METHOD == D2D_METHOD_IMAGE) ? 1 : 0;  // both grid roles
     const cudaError_t e = launch_tiles(kern, q, q.macro != 0, smem, stream, q, out);
     return e != cudaSuccess ? (int)e : (int)cudaGetLastError();
 }

@@ -132,7 +132,7 @@ __device__ __forceinline__ float path_loss(const SceneTab& T, const Cand<K>& cd,
 // first arg-max in the reference's (segment, object) order.
 // Fast path per test: canonical a, b, d; approximate parameters through one MUFU.RCP and two FMAs; the exact
 // IEEE divisions (hit_exact, out of line) only run when the test could raise the running maximum `interx`.
-// `hint` (forward-style calls only, TRACK = false): a per-warp slot holding the object that blocked the warp's previous
+// `hint` (optional): a per-warp slot holding the object that blocked the warp's previous
 // path.  The fold then starts there and wraps around: neighbouring candidates and receivers are mostly blocked by the
 // same wall, and a blocked path leaves the loop at its blocker (95 % of the paths that reach the fold are blocked; in
 // list order they scan half the scene first).  max is exact and commutative, so the value does not depend on the order.
@@ -152,7 +152,7 @@ __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, co
         sb[i] = (i < K) ? cd.c[i < K ? i : 0] : -1;
     }
     int j0 = 0, blocker = -1;
-    if (!TRACK && hint) {
+    if (hint) {
         j0 = *reinterpret_cast<volatile int*>(hint);
         if (j0 >= N) j0 = 0;
     }
@@ -172,24 +172,29 @@ __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, co
             const float qa = fmaf(a, r, -0.5f);
             const float qb = fmaf(b, r, -0.5f);
             const float m = fmaxf(fabsf(qa), fabsf(qb));
+            if (!TRACK) D2D_COUNT(27);
             if (!(m >= cthr)) {
+                if (!TRACK) D2D_COUNT(28);
                 const float hx = hit_exact(a, b, d);
-                if (hx > interx || (TRACK && hx == interx && i < arg_seg)) {
+                // ties between tests (TRACK: the reverse sweep follows ONE arg-max): the first in the reference's
+                // (segment, object) order wins, whatever order this fold visits the objects in
+                if (hx > interx || (TRACK && hx == interx && (i < arg_seg || (i == arg_seg && j < arg_j)))) {
                     interx = hx;
                     if (TRACK) { arg_j = j; arg_seg = i; }
                     cthr = filter_threshold(fmaxf(hx, xz));
                     // the path is dead once `intersects` is exactly true / 1.0
                     if (MODE == D2D_MODE_HARD) alive = !(hx >= 0.0f);
-                    else alive = !(act<MODE>(hx, alpha) == 1.0f);
+                    else alive = !act_is_one<MODE>(hx, alpha);
                 }
             }
         }
         if (!alive) {
             blocker = j;
+            if (!TRACK) { D2D_COUNT(26); if (jj == 0) D2D_COUNT(25); }
             break;
         }
     }
-    if (!TRACK && hint && blocker >= 0) *reinterpret_cast<volatile int*>(hint) = blocker;  // (any lane's: a heuristic)
+    if (hint && blocker >= 0) *reinterpret_cast<volatile int*>(hint) = blocker;  // (any lane's: a heuristic)
     return interx;
 }
 
@@ -229,17 +234,19 @@ __device__ __forceinline__ float validity_from_onx(const SceneTab& T, const KPar
         if (a_on == 0.0f) return 0.0f;
     }
     // 2. loss below tolerance
+    D2D_COUNT(22);
     if (LAZY_LOSS) loss = path_loss<K>(T, cd, X);
     const float lx = p.tol - loss;
     float a_l = 1.0f;
     if (MODE == D2D_MODE_HARD) {
-        if (!(lx > 0.0f)) return 0.0f;
+        if (!(lx > 0.0f)) { D2D_COUNT(23); return 0.0f; }
     } else {
         if (lx != lx) return 0.0f;  // nan_to_num
         a_l = act<MODE>(lx, alpha);
-        if (a_l == 0.0f) return 0.0f;
+        if (a_l == 0.0f) { D2D_COUNT(23); return 0.0f; }
     }
     // 3. occlusion
+    D2D_COUNT(24);
     bool alive = true;
     int seg = 0, jj = 0;
     const float interx = intersects_x<MODE, K, false>(T, p.N, cd, X, alpha, alive, seg, jj, hint);

@@ -268,6 +268,7 @@ def path_length(points):
 
 def segments_intersect(P1, P2, P3, P4, logic: Logic, tol=0.005):
     """geometry.py:82-173 (Graphics Gems III).  All points broadcast over leading dims."""
+    hi = _c(np.float32(1.0) + np.float32(tol))  # fl32(1 + tol): a constant folded in fp32 by the reference's trace
     tol = _c(tol)
     A = P2 - P1
     B = P3 - P4
@@ -281,11 +282,11 @@ def segments_intersect(P1, P2, P3, P4, logic: Logic, tol=0.005):
         den = torch.where(den_is_zero, torch.ones_like(den), den)
         if CLEAN and logic.approx:
             t = num / den
-            res = logic.land(logic.ge(t, -tol), logic.le(t, 1.0 + tol))
+            res = logic.land(logic.ge(t, -tol), logic.le(t, hi))
             # t = +inf gives ge -> 1, le -> 0, and -> 0 : a constant
             return torch.where(den_is_zero, torch.zeros_like(res), res)
         t = torch.where(den_is_zero, torch.full_like(den, float("inf")), num / den)
-        return logic.land(logic.ge(t, -tol), logic.le(t, 1.0 + tol))
+        return logic.land(logic.ge(t, -tol), logic.le(t, hi))
 
     return logic.land(test(a, d), test(b, d))
 

@@ -62,6 +62,27 @@ def main():
         cfg = F.TraceConfig(mode="hard", max_order=1, grid_cols=100)
         ms = timed(lambda: F.power_fwd(cfg, xys, fixed, grid, device="cuda"), a.steps)
         emit("cfg1: obstacle scene, ImagePath orders 0-1, 100x100, hard, forward", ms, 1e4 * ncand(8, 0, 1))
+    if want("txgrid"):
+        # the reference's own benchmark workload (tests/benchmarks/test_scene.py:9-29): accumulate_on_transmitters_grid_
+        # over_paths on basic_scene, beside the receivers role on the same scene and grid
+        sc = d.Scene.basic_scene()
+        xys, kinds, phis = sc.packed_objects()
+        for n in (50, 1024):
+            X, Y = sc.grid(n, n)
+            grid = torch.from_numpy(np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)).cuda()
+            for approx, mode in ((False, "hard"), (True, "hard_sigmoid")):
+                for order in (1, 2):
+                    res = {}
+                    for role, src in (("receivers", sc.transmitters), ("transmitters", sc.receivers)):
+                        fixed = np.stack([p.xy for p in src.values()])
+                        for cull in (True, False):
+                            cfg = F.TraceConfig(mode=mode, max_order=order, grid_cols=n, grid_role=role, cull=cull)
+                            res[(role, cull)] = timed(lambda: F.power_fwd(cfg, xys, fixed, grid, device="cuda"), a.steps)
+                    emit(f"txgrid: basic_scene, ImagePath orders 0-{order}, {n}x{n}, approx={approx}, forward",
+                         res[("transmitters", True)], n * n * ncand(7, 0, order),
+                         rx_grid_ms=res[("receivers", True)], tx_grid_nocull_ms=res[("transmitters", False)],
+                         rx_grid_nocull_ms=res[("receivers", False)],
+                         tx_over_rx=res[("transmitters", True)] / res[("receivers", True)])
     if want("cfg2"):
         sc = d.Scene.square_scene_with_obstacle()
         xys, kinds, phis, fixed, grid = pack(sc, 1024)

@@ -9,7 +9,9 @@ NAMES = {0: "tile-cull evaluations", 1: "rule 1 last interaction", 2: "rule 1 ea
          4: "rule 3 zero-length", 5: "rule 2 wrong side", 6: "tile survivors", 7: "  survivors with zero-length wall, not provably dead",
          8: "  kept: u.n changes sign", 9: "  kept: NaN", 10: "  kept: u.n near zero", 11: "rule 1' evaluated, kept", 12: "rule 1' not applicable",
          20: "macro-tile tests (cluster stage)", 21: "  macro survivors", 13: "warp-cull tests", 14: "warp-cull kept (= warp visits)", 16: "thread visits", 17: "thread passes on_objects",
-         18: "  of which with zero-length wall", 19: "thread valid != 0"}
+         18: "  of which with zero-length wall", 22: "thread evaluates the loss", 23: "  killed by the loss",
+         24: "thread enters the occlusion fold", 26: "  killed by the fold", 25: "    at the first object tested (the hint)",
+         27: "fold: (segment, object) tests", 28: "fold:   of which reach the exact divisions", 19: "thread valid != 0"}
 lib = L.lib()
 lib.d2d_debug_counters.argtypes = [C.c_int32, C.c_void_p, C.c_int32]
 for coords in ("raw", "normalised"):

@@ -60,9 +60,11 @@ def test_vjp_raw_geojson_bench_config(mode, alpha):
     else:
         assert np.array_equal(v, vc), f"{int((v != vc).sum())} of {v.size} validity values differ from the C oracle"
     assert (vc != 0).sum() > 0
-    # 2. + 3. value and cotangents
+    # 2. + 3. value and cotangents: two INDEPENDENT fp32 oracles (reverse mode: torch autograd over the restated graph;
+    # forward mode: dual numbers over the scalar C++ port) and the fp64 evaluation of the same function
     Zo, go = _oracle_vjp(sc, X, Y, Zbar, mode, alpha)
     Z64, g64 = _oracle_vjp64(sc, X, Y, Zbar, mode, alpha)
+    ad = CO.power_vjp(xys, fixed, grid, Zbar, max_order=2, mode=mode, alpha=alpha)
     out = F.power_value_and_vjp(_cfg(mode, max_order=2, reduce_all=True, grid_cols=X.shape[1]), xys, fixed, grid,
                                 Zbar.reshape(-1), alpha=alpha, device="cuda")
     out = {k: t.cpu().numpy() for k, t in out.items()}
@@ -75,14 +77,19 @@ def test_vjp_raw_geojson_bench_config(mode, alpha):
         got = out[key].reshape(-1).astype(np.float64)
         w32 = go[okey].numpy().reshape(-1).astype(np.float64)
         w64 = g64[okey].numpy().reshape(-1).astype(np.float64)
+        a32 = ad[key].reshape(-1)
         scale = max(np.abs(w32).max(), 1e-30)
-        agree = np.abs(w32 - w64) <= 1e-3 * np.abs(w64) + 1e-6 * scale  # the oracle is well conditioned here
+        # well conditioned in fp32 = BOTH fp32 oracles reproduce the fp64 value to 1e-3 (one alone can agree by chance)
+        agree = (np.abs(w32 - w64) <= 1e-3 * np.abs(w64) + 1e-6 * scale) & (np.abs(a32 - w64) <= 1e-3 * np.abs(w64) + 1e-6 * scale)
         tol = 1e-4 * np.abs(w32) + 1e-6 * scale
         bad = (np.abs(got - w32) > tol) & agree
         assert not bad.any(), (f"{key}_bar: {int(bad.sum())} of {int(agree.sum())} well-conditioned entries miss rtol 1e-4; "
                                f"worst |diff| {np.abs(got - w32)[bad].max():.3g} at scale {scale:.3g}")
-        n_esc = _close(got, w32, 1e-4, f"{key}_bar (raw lon/lat)", w64, max_escaped=1.0)
-        report.append(f"{key}: {int((~agree).sum())}/{agree.size} ill-conditioned in fp32, {n_esc} accepted via fp64 leg")
+        # everywhere else: no farther from the fp32 oracle than the fp32 oracles are from fp64 / from each other
+        noise = np.maximum(np.abs(w32 - w64), np.abs(a32 - w32))
+        still = np.abs(got - w32) > tol + 4.0 * noise + 4.0 * np.percentile(noise, 90)
+        assert not still.any(), f"{key}_bar: {int(still.sum())} entries exceed the oracles' own fp32 noise"
+        report.append(f"{key}: {int((~agree).sum())}/{agree.size} ill-conditioned in fp32")
     print(f"[parity] raw geojson {mode} alpha={alpha:g}: " + "; ".join(report))
 
 
@@ -448,3 +455,69 @@ def test_host_entry_is_reentrant_across_threads():
     [t.start() for t in ts]
     [t.join() for t in ts]
     assert not errs, errs
+
+
+# ---- transmitters-grid cull ---------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["basic", "obstacle", "wall", "geojson_norm", "geojson"])
+@pytest.mark.parametrize("alpha", [1.0, 10.0, 100.0, 1000.0])
+def test_transmitters_grid_cull_equals_nocull(name, alpha):
+    """The tile / macro-tile cull of the transmitters-grid role (csrc/d2d_driver.cuh: tile_may_be_valid_tx, the receiver
+    unfolded through the candidate, s-range rule on every interaction with the error recursion of the thread's own image
+    chain) must not change a single bit of the map or of the per-point cotangents: every scene, every logic, the alpha
+    sweep, bbox grids (points ON the walls), two receivers, orders 0-2."""
+    sc = SCENES[name]
+    sc = sc.update_receivers(rx2=d.Point(xy=sc.center() + np.float32(0.31) * (sc.bounding_box()[1] - sc.center())))
+    n = 512 if name.startswith("geojson") else 384
+    X, Y = sc.grid(n, n)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.receivers.values()])
+    for mode in ("hard", "hard_sigmoid", "sigmoid"):
+        if mode == "hard" and alpha != 100.0:
+            continue
+        kw = dict(max_order=2, grid_cols=n, grid_role="transmitters")
+        a = F.power_fwd(_cfg(mode, **kw), xys, fixed, grid, alpha=alpha, device="cuda")
+        b = F.power_fwd(_cfg(mode, cull=False, **kw), xys, fixed, grid, alpha=alpha, device="cuda")
+        assert torch.equal(a, b), (mode, int((a != b).sum()))
+        assert float(a.abs().max()) > 0
+        ga = F.power_bwd(_cfg(mode, reduce_all=True, **kw), xys, fixed, grid, None, alpha=alpha, device="cuda")
+        gb = F.power_bwd(_cfg(mode, reduce_all=True, cull=False, **kw), xys, fixed, grid, None, alpha=alpha, device="cuda")
+        assert torch.equal(ga["Z"], gb["Z"]) and torch.equal(ga["grid"], gb["grid"]), mode
+        for k in ("objects", "fixed", "alpha"):  # fp32 atomics: order not fixed
+            scale = max(gb[k].abs().max().item(), 1e-30)
+            assert torch.allclose(ga[k], gb[k], rtol=1e-3, atol=1e-4 * scale), (mode, k)
+
+
+@pytest.mark.parametrize("name", ["basic", "geojson_norm"])
+def test_transmitters_grid_cull_order3_and_flat_tiles(name):
+    """Three-interaction chains (every stage of the unfolded test), 1-D tiles (grid_cols = 0) and a jittered grid."""
+    sc = SCENES[name]
+    n = 96 if name.startswith("geojson") else 192
+    X, Y = H.jittered_grid(sc, n, n, seed=5)
+    grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.receivers.values()])
+    for mode in ("hard", "hard_sigmoid", "sigmoid"):
+        for cols in (n, 0):
+            kw = dict(min_order=3, max_order=3, grid_cols=cols, candidate_slices=1, grid_role="transmitters")
+            a = F.power_fwd(_cfg(mode, **kw), xys, fixed, grid, alpha=100.0, device="cuda")
+            b = F.power_fwd(_cfg(mode, cull=False, **kw), xys, fixed, grid, alpha=100.0, device="cuda")
+            assert torch.equal(a, b), (mode, cols, int((a != b).sum()))
+
+
+def test_transmitters_grid_cull_random_scenes():
+    """Random short walls in generic position (many orientations, many near-grazing incidences), hard logic masks bit
+    for bit against the C oracle with the cull on."""
+    from tests.test_gpu_parity import _random_walls
+
+    for seed in (1, 2, 3):
+        sc = _random_walls(24, seed=seed, length=0.25)
+        X, Y = sc.grid(64, 48)
+        grid = np.stack([X, Y], -1).reshape(-1, 2).astype(np.float32)
+        xys, _, _ = sc.packed_objects()
+        fixed = np.stack([p.xy for p in sc.receivers.values()])
+        Z, v = F.power_fwd(_cfg("hard", max_order=2, grid_cols=64, grid_role="transmitters"), xys, fixed, grid,
+                           want_valid=True, device="cuda")
+        Zc, vc = CO.power_map(xys, fixed, grid, grid_role="transmitters", max_order=2, mode="hard", want_valid=True)
+        assert np.array_equal(v.cpu().numpy(), vc) and np.array_equal(Z.cpu().numpy(), Zc)
+        assert vc.sum() > 0

@@ -337,3 +337,60 @@ def test_oracles_reproduce_the_golden_fixtures(name):
     for k in ("grid", "xys", "fixed", "alpha"):
         want = g[f"{name}/vjp/{k}_bar"]
         np.testing.assert_allclose(gr[k].numpy(), want, rtol=1e-5, atol=1e-6 * max(np.abs(want).max(), 1e-30), err_msg=k)
+
+
+@pytest.mark.parametrize("name", ["obstacle", "basic", "geojson_norm"])
+def test_dual_number_oracle_reproduces_the_golden_vjp(name):
+    """oracle/d2d_oracle_ad.cpp (forward-mode AD over the scalar port) against the committed vectors, which were
+    produced by torch REVERSE-mode autograd over oracle/ref_torch.py: two independent differentiation mechanisms over two
+    independent restatements.  Forward value bit for bit with the C oracle; cotangents to 1e-5 (fp32) and the fp64
+    evaluation against the committed fp64 leg to 1e-7 (summation order)."""
+    from oracle import c_oracle as CO
+
+    g = _golden()
+    X, Y, xys, fixed = g[f"{name}/X"], g[f"{name}/Y"], g[f"{name}/xys"], g[f"{name}/fixed"]
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    Zbar = g[f"{name}/vjp/Zbar"]
+    a = CO.power_vjp(xys, fixed, grid, Zbar, max_order=2, mode="hard_sigmoid", alpha=20.0)
+    Zc = CO.power_map(xys, fixed, grid, max_order=2, mode="hard_sigmoid", alpha=20.0, reduce_all=True)
+    assert np.array_equal(a["Z"].astype(np.float32), Zc)
+    a64 = CO.power_vjp(xys, fixed, grid, Zbar, max_order=2, mode="hard_sigmoid", alpha=20.0, real64=True)
+    for k, ko in (("grid", "grid"), ("objects", "xys"), ("fixed", "fixed"), ("alpha", "alpha")):
+        want = g[f"{name}/vjp/{ko}_bar"].astype(np.float64).reshape(-1)
+        want64 = g[f"{name}/vjp64/{ko}_bar"].reshape(-1)
+        scale = max(np.abs(want64).max(), 1e-30)
+        if not (name == "basic" and k == "objects"):  # (axis-aligned scene: structural min/max ties, DESIGN.md "Ties")
+            np.testing.assert_allclose(a[k].reshape(-1), want, rtol=1e-5, atol=2e-6 * scale, err_msg=f"{k} fp32")
+            np.testing.assert_allclose(a64[k].reshape(-1), want64, rtol=1e-7, atol=1e-9 * scale, err_msg=f"{k} fp64")
+
+
+def test_dual_number_oracle_other_roles_and_objects():
+    """Transmitters-grid role, RIS angle cotangent, sigmoid, hard logic: dual numbers vs torch autograd."""
+    import differt2d_b200 as d
+    from oracle import c_oracle as CO
+    from oracle import ref_torch as R
+    from tests import helpers as H
+
+    sc = H.generic_position(d.Scene.square_scene().add_objects(
+        d.RIS(xys=[[0.5, 0.3], [0.5, 0.7]], phi=float(np.pi / 4)), d.Wall(xys=[[0.7, 0.15], [0.9, 0.35]])))
+    sc = sc.update_receivers(rx2=d.Point(xy=[0.8, 0.3]))
+    X, Y = H.jittered_grid(sc, 6, 7, seed=3)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    Zbar = np.random.default_rng(7).standard_normal(X.shape).astype(np.float32)
+    osc = H.oracle_scene_from_product(sc)
+    for role, mode, alpha in (("receivers", "hard_sigmoid", 2.0), ("transmitters", "sigmoid", 3.0), ("receivers", "hard", 100.0)):
+        src = sc.transmitters if role == "receivers" else sc.receivers
+        fixed = np.stack([p.xy for p in src.values()])
+        a = CO.power_vjp(xys, fixed, grid, Zbar, kinds=kinds, phis=phis, grid_role=role, max_order=2, mode=mode, alpha=alpha)
+        with R.clean_gradients():
+            Zo, go = R.power_map_and_vjp(osc, X, Y, Zbar, grid_role=role, max_order=2, approx=mode != "hard", alpha=alpha,
+                                         function="sigmoid" if mode == "sigmoid" else "hard_sigmoid")
+        np.testing.assert_allclose(a["Z"].reshape(X.shape), Zo.numpy(), rtol=1e-6, atol=1e-7)
+        for k, ko in (("grid", "grid"), ("objects", "xys"), ("phis", "phis"), ("fixed", "fixed"), ("alpha", "alpha")):
+            want = go[ko].numpy().astype(np.float64).reshape(-1)
+            scale = max(np.abs(want).max(), 1e-30)
+            np.testing.assert_allclose(a[k].reshape(-1), want, rtol=2e-5, atol=2e-6 * scale, err_msg=f"{role} {mode} {k}")
+        if mode != "hard" and role == "receivers":
+            assert np.abs(a["phis"]).max() > 0
