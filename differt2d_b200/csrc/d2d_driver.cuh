@@ -425,18 +425,28 @@ __device__ __forceinline__ bool tile_may_be_valid_tx(const SceneTab& T, const in
     for (int i = 0; i < K; ++i) { simx = fmaxf(simx, fabsf(R[i].x)); simy = fmaxf(simy, fabsf(R[i].y)); }
     // rounding of ONE mirror (p - 2 ((p - P1).n) n with |p - P1| <= (2 K + 1) diam): lattice + relative terms
     const float e1 = 1.5f * eps * pow2_floor(fmaxf(simx, simy)) + 16.0f * eps * (2.0f * K + 1.0f) * diam;
+    // Frames.  At the stage next to the receiver (i = K - 1) the thread's back-projection IS this evaluation (same centre
+    // rx, same apex up to rounding).  At an earlier stage the thread projects from ITS previous point X_{i+2}, which lies
+    // on this evaluation's line at the fraction (1 + g') of the way from the apex to the unfolded receiver (g' = this
+    // evaluation's g at stage i + 1): the thread's u and u.n are this frame's times (1 + g'), its g is (g - g') / (1 + g').
+    // When 1 + g' approaches 0 (the previous point falls onto the image itself: e.g. a transmitter ON the next wall's
+    // line) the thread's u.n vanishes, its masked branch (geometry.py:1105) or an unbounded error takes over, and
+    // nothing can be said from here: keep the candidate.
     float Enext = 0.0f;
+    float opg_prev = 1.0f, gabs_prev = 0.0f;
+    bool first = true;
 #pragma unroll
     for (int i = K - 1; i >= 0; --i) {
         const int j = c[i];
         const float4 w0 = T.w0[j];
         const float4 w1 = T.w1[j];
         const int kind = T.kind[j];
-        if (kind == D2D_KIND_VERTEX) continue;            // X = previous point, always on the object
-        if (w0.z == 0.0f && w0.w == 0.0f) continue;        // zero-length object: n = 0, X = previous point, s = 0
+        // (a Vertex or a zero-length object leaves the previous point where it is: X = previous point in both frames;
+        // the frame relation above would need the stage before it, so the cull stops refining here)
+        if (kind == D2D_KIND_VERTEX || (w0.z == 0.0f && w0.w == 0.0f)) break;
         const float EI = (float)(i + 1) * e1;              // the thread's (and this evaluation's) image of level i + 1
         const float ER = (float)(K - 1 - i) * e1;          // this evaluation's unfolded receiver
-        float smin = CUDART_INF_F, smax = -CUDART_INF_F, gabs = 0.f;
+        float smin = CUDART_INF_F, smax = -CUDART_INF_F, gabs = 0.f, opg = CUDART_INF_F;
         float unmin = CUDART_INF_F, U1 = 0.f, V1 = 0.f, uxm = 0.f, uym = 0.f, u2m = 0.f;
         int pos = 0, neg = 0;
         const float rtt = rcp_approx(w1.z);
@@ -455,6 +465,7 @@ __device__ __forceinline__ bool tile_may_be_valid_tx(const SceneTab& T, const in
             const float sq = fmaf(w0.z, Dx, w0.w * Dy) * rtt;
             smin = fminf(smin, sq); smax = fmaxf(smax, sq);
             gabs = fmaxf(gabs, fabsf(g));
+            opg = fminf(opg, fabsf(1.0f + g));
             unmin = fminf(unmin, fabsf(un));
             U1 = fmaxf(U1, fabsf(ux) + fabsf(uy));
             V1 = fmaxf(V1, fabsf(vx) + fabsf(vy));
@@ -463,24 +474,33 @@ __device__ __forceinline__ bool tile_may_be_valid_tx(const SceneTab& T, const in
         }
         u2m = sqrt_approx(u2m) * 1.000001f;
         if (!(pos == 4 || neg == 4)) return true;                          // u.n may vanish inside the tile
-        if (!(smin == smin) || !(smax == smax) || !(gabs == gabs)) return true;
-        if (!(unmin > 64.0f * eps * U1 + 4.0f * (EI + ER + Enext))) return true;  // u.n not reliably away from zero
+        if (!(smin == smin) || !(smax == smax) || !(gabs == gabs) || !(opg == opg)) return true;
         gabs *= 1.000001f;
+        // the thread's frame at this stage
+        const float f = first ? 1.0f : opg_prev;
+        const float unminT = f * unmin;
+        if (!(unmin > 64.0f * eps * U1 + 4.0f * (EI + ER))) return true;           // this frame's u.n not reliable
+        if (!(unminT > 64.0f * eps * U1 * fmaxf(f, 1.0f) + 8.0f * (EI + Enext))) return true;  // the thread's u.n not reliable
         const float run = rcp_approx(unmin) * 1.000001f;
-        const float lip = (1.0f + gabs) * (1.0f + u2m * run);
-        const float gu1 = gabs * u2m, gu5 = 5.0f * gu1;
-        // the thread's back-projection: |v|_1 <= 2 diam
-        const float ampT = 4.4f * (2.0f * diam + gabs * U1) * run;
-        const float relTx = eps * (0.8f * gu5 + 4.0f * gabs * uxm + ampT * uxm + 4.0f * diam);
-        const float relTy = eps * (0.8f * gu5 + 4.0f * gabs * uym + ampT * uym + 4.0f * diam);
-        const float devT = 1.5f * lip * (Enext + EI);
-        const float dTx = eps * pow2_floor(scale_x + gu1) + relTx + devT;
-        const float dTy = eps * pow2_floor(scale_y + gu1) + relTy + devT;
+        const float rho = u2m * run;                                               // |u| / |u.n|: the same in both frames
+        const float gsum = first ? gabs : (gabs + gabs_prev);
+        const float gabsT = first ? gabs : gsum * rcp_approx(f) * 1.000001f;       // |g_thread| <= (|g| + |g'|) / |1 + g'|
+        const float ellT = gsum * u2m;                                             // |g_thread| |u_thread|
+        const float lipT = (1.0f + gabsT) * (1.0f + rho);
+        const float lipC = (1.0f + gabs) * (1.0f + rho);
+        // the thread's back-projection: |v|_1 <= 2 diam, |u_c| / |u.n| frame invariant
+        const float ampT = 4.4f * (2.0f * diam + 1.5f * ellT) * run;
+        const float relTx = eps * (8.0f * ellT + ampT * uxm + 4.0f * diam);
+        const float relTy = eps * (8.0f * ellT + ampT * uym + 4.0f * diam);
+        const float devT = 1.5f * lipT * (Enext + EI);
+        const float dTx = eps * pow2_floor(scale_x + ellT) + relTx + devT;
+        const float dTy = eps * pow2_floor(scale_y + ellT) + relTy + devT;
         // this evaluation: relative terms with ITS v, and the rounding of its two images
+        const float gu1 = gabs * u2m;
         const float ampC = 4.4f * (V1 + gabs * U1) * run;
-        const float relCx = eps * (0.8f * gu5 + 4.0f * gabs * uxm + ampC * uxm + 2.0f * V1);
-        const float relCy = eps * (0.8f * gu5 + 4.0f * gabs * uym + ampC * uym + 2.0f * V1);
-        const float devC = 1.5f * lip * (EI + ER);
+        const float relCx = eps * (4.0f * gu1 + 4.0f * gabs * uxm + ampC * uxm + 2.0f * V1);
+        const float relCy = eps * (4.0f * gu1 + 4.0f * gabs * uym + ampC * uym + 2.0f * V1);
+        const float devC = 1.5f * lipC * (EI + ER);
         const float smag = fmaxf(fabsf(smin), fabsf(smax));
         const float ds = (fabsf(w0.z) * (dTx + relCx + devC) + fabsf(w0.w) * (dTy + relCy + devC)) * (rtt * 1.000001f) +
                          16.0f * eps * smag;
@@ -488,6 +508,10 @@ __device__ __forceinline__ bool tile_may_be_valid_tx(const SceneTab& T, const in
         if (!(tol < CUDART_INF_F)) return true;
         if (smax < xz - tol || smin > 1.0f - xz + tol) { D2D_COUNT(i == K - 1 ? 1 : 2); return false; }  // rule (1)
         Enext = fmaxf(dTx, dTy) * 1.25f;  // the thread's X_{i+1}
+        // |1 + g| over the tile, less what the rounding of g can take away
+        opg_prev = opg - (8.0f * eps * (1.0f + gabs) + 2.0f * (EI + ER) * run * (1.0f + gabs));
+        gabs_prev = gabs;
+        first = false;
     }
     D2D_COUNT(6);
     return true;

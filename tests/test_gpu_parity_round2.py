@@ -521,3 +521,51 @@ def test_transmitters_grid_cull_random_scenes():
         Zc, vc = CO.power_map(xys, fixed, grid, grid_role="transmitters", max_order=2, mode="hard", want_valid=True)
         assert np.array_equal(v.cpu().numpy(), vc) and np.array_equal(Z.cpu().numpy(), Zc)
         assert vc.sum() > 0
+
+
+# ---- Fermat / MinPath at the default steps = 100: how far can two fp32 implementations agree? --------
+@pytest.mark.parametrize("method", ["fermat", "minpath"])
+@pytest.mark.parametrize("mode", ["hard", "hard_sigmoid"])
+def test_solver_steps100_distance_is_within_the_oracles_own_fp32_noise(method, mode):
+    """
+    optimize.minimize (optimize.py:83-97) with the reference's default steps = 100, forward AND VJP through the scan.
+    Near convergence Adam's update m / (sqrt(v) + eps) is a ratio of vanishing quantities: the 100th iterate and, much
+    more so, its derivative amplify last-bit differences.  That was a claim in round 1; here it is measured: the same
+    oracle graph evaluated in fp64 (ref_torch.precision) is the yardstick.  For every output the distance between the
+    CUDA kernels and the fp32 oracle must not exceed 4 x the distance between the fp32 oracle and its own fp64
+    evaluation (+ the elementwise bar), i.e. the kernels are as close to the reference's fp32 graph as that graph is to
+    the function it computes.  Both distances are printed.
+    """
+    from tests.test_gpu_parity import _vertex_scene
+
+    sc = H.generic_position(_vertex_scene())
+    osc = H.oracle_scene_from_product(sc)
+    X, Y = H.jittered_grid(sc, 4, 5, seed=3)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    C = 1 + 7 + 42
+    x0 = np.random.default_rng(1234).random((C, 2), dtype=np.float32)
+    Zbar = (0.5 + np.random.default_rng(7).random(X.shape)).astype(np.float32)
+    cfg = _cfg(mode, max_order=2, method=method, steps=100, grid_cols=X.shape[1], reduce_all=True)
+    got = F.power_bwd(cfg, xys, fixed, grid, Zbar.reshape(-1), kinds=kinds, phis=phis, x0=x0, alpha=100.0, device="cuda")
+    kw = dict(method=method, max_order=2, x0=x0, steps=100, approx=mode != "hard", alpha=100.0, function="hard_sigmoid")
+    Z32, g32 = R.power_map_and_vjp(osc, X, Y, Zbar, **kw)
+    with R.precision("f64"):
+        Z64, g64 = R.power_map_and_vjp(osc, X, Y, Zbar, **kw)
+    legs = {"Z": (got["Z"], Z32, Z64), "grid": (got["grid"], g32["grid"], g64["grid"]),
+            "objects": (got["objects"], g32["xys"], g64["xys"]), "fixed": (got["fixed"], g32["fixed"], g64["fixed"])}
+    if mode != "hard":
+        legs["alpha"] = (got["alpha"], g32["alpha"], g64["alpha"])
+    report = []
+    for k, (a, w32, w64) in legs.items():
+        a = a.cpu().numpy().reshape(-1).astype(np.float64)
+        w32 = w32.detach().numpy().reshape(-1).astype(np.float64)
+        w64 = w64.detach().numpy().reshape(-1).astype(np.float64)
+        scale = max(np.abs(w64).max(), 1e-30)
+        d_kernel = np.abs(a - w32).max() / scale
+        d_oracle = np.abs(w32 - w64).max() / scale
+        report.append(f"{k}: kernel-vs-fp32 {d_kernel:.2e}, fp32-vs-fp64 {d_oracle:.2e}")
+        assert d_kernel <= 4.0 * d_oracle + 1e-4, f"{method} {mode} {k}: {report[-1]}"
+    print(f"[parity] {method} {mode} steps=100: " + "; ".join(report))
