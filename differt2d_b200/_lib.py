@@ -84,7 +84,7 @@ class D2DPathRecord(C.Structure):
 
 EXPORTS = [
     "d2d_problem_defaults", "d2d_candidates_count", "d2d_candidates_host", "d2d_candidates_device",
-    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_paths", "d2d_power_host", "d2d_host_release", "d2d_launch_count",
+    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_paths", "d2d_power_host", "d2d_host_release", "d2d_sanitise_scene", "d2d_affine_points", "d2d_launch_count",
     "d2d_fma_peak_launch", "d2d_last_error", "d2d_abi_version",
 ]
 
@@ -124,6 +124,11 @@ def lib() -> C.CDLL:
     L.d2d_power_bwd.restype = C.c_int
     L.d2d_power_host.argtypes = [P, vp, vp, vp, vp, vp, vp, vp, C.c_int32]
     L.d2d_power_host.restype = C.c_int
+    if hasattr(L, "d2d_sanitise_scene") or not os.environ.get("D2D_B200_LIB"):  # (older diagnostic builds lack it)
+        L.d2d_sanitise_scene.argtypes = [vp, vp, vp, C.c_int32, vp, C.c_int64, C.c_int32, C.c_int32, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.d2d_sanitise_scene.restype = C.c_int
+        L.d2d_affine_points.argtypes = [vp, C.c_int64, vp, vp, vp]
+        L.d2d_affine_points.restype = C.c_int
     L.d2d_host_release.argtypes = []
     L.d2d_host_release.restype = None
     L.d2d_launch_count.argtypes = []

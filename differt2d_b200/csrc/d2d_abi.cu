@@ -344,6 +344,30 @@ int d2d_paths(const D2DProblem* p, float min_valid, int32_t emit_all, D2DPathRec
     return e == 0 ? D2D_OK : cuda_fail(e, "paths_kernel");
 }
 
+int d2d_sanitise_scene(const float* xys, const uint8_t* kinds, const float* phis, int32_t n, const float* points,
+                       int64_t n_points, int32_t drop_zero_length, int32_t normalise, float* xys_out, uint8_t* kinds_out,
+                       float* phis_out, int32_t* kept_index, int32_t* n_kept, uint8_t* flags, double* affine, void* stream) {
+    if (n < 0 || n > D2D_MAX_OBJECTS) return fail(D2D_ERR_UNSUPPORTED, "n outside [0, D2D_MAX_OBJECTS]");
+    if ((n > 0 && (!xys || !xys_out)) || n_points < 0 || (n_points > 0 && !points))
+        return fail(D2D_ERR_INVALID_ARGUMENT, "xys / xys_out / points is NULL");
+    if (normalise && !affine) return fail(D2D_ERR_INVALID_ARGUMENT, "normalise needs the affine output (the map back)");
+    long long nl = 0;
+    const int e = d2d::launch_sanitise(xys, kinds, phis, n, points, n_points, drop_zero_length ? 1 : 0, normalise ? 1 : 0,
+                                       xys_out, kinds_out, phis_out, kept_index, n_kept, flags, affine,
+                                       (cudaStream_t)stream, &nl);
+    g_launches += nl;
+    return e == 0 ? D2D_OK : cuda_fail(e, "sanitise_objects_kernel");
+}
+
+int d2d_affine_points(const float* points, int64_t n_points, const double* affine, float* points_out, void* stream) {
+    if (n_points < 0 || (n_points > 0 && (!points || !points_out || !affine)))
+        return fail(D2D_ERR_INVALID_ARGUMENT, "points / points_out / affine is NULL");
+    long long nl = 0;
+    const int e = d2d::launch_affine_points(points, n_points, affine, points_out, (cudaStream_t)stream, &nl);
+    g_launches += nl;
+    return e == 0 ? D2D_OK : cuda_fail(e, "affine_points_kernel");
+}
+
 // ---- host-buffer entry ---------------------------------------------------------------------------
 namespace {
 constexpr int kHostStreams = 3;

@@ -38,6 +38,14 @@ int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, floa
 int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, const float* Zbar, const BwdOut& out,
                      cudaStream_t stream, long long* launches);
 
+// scene sanitiser (d2d_sanitise.cu)
+int launch_sanitise(const float* xys, const uint8_t* kinds, const float* phis, int n, const float* points,
+                    long long n_points, int drop, int normalise, float* xys_out, uint8_t* kinds_out, float* phis_out,
+                    int32_t* kept_index, int32_t* n_kept, uint8_t* flags, double* affine, cudaStream_t stream,
+                    long long* launches);
+int launch_affine_points(const float* in, long long n, const double* affine, float* out, cudaStream_t stream,
+                         long long* launches);
+
 // D2D_GRAD_NAN_PARITY: overwrites with NaN the cotangents the reference's literal graph poisons (d2d_nan.cu)
 int launch_nan_poison(const KParams& p, int mode, int grid_role, const BwdOut& out, cudaStream_t stream,
                       long long* launches);

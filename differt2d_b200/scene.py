@@ -141,7 +141,7 @@ class Scene:
                 rx=Point(xy=Scene(objects=walls).get_location(rx_loc)))
         return sc.with_transmitters(tx=Point(xy=[0.0, 0.0])).with_receivers(rx=Point(xy=[1.0, 1.0]))
 
-    def sanitised(self, drop_zero_length: bool = True, normalise: bool = False, return_map: bool = False):
+    def sanitised(self, drop_zero_length: bool = True, normalise: bool = False, return_map: bool = False, device=None):
         """
         SURVEY §8 (f)2 — a scene the fp32 path tracer is well conditioned on (NOT part of the reference: results
         differ from the raw scene's, which stays the parity case).
@@ -156,7 +156,13 @@ class Scene:
 
         ``return_map``: also returns ``{"kept": indices of the kept objects, "origin": [2], "scale": float}`` so that
         cotangents w.r.t. the sanitised vertices can be carried back (d/d raw = d/d sanitised / scale).
+
+        ``device``: a CUDA device — the object table is then built by the library's sanitiser kernel
+        (``d2d_sanitise_scene`` / ``d2d_affine_points``, csrc/d2d_sanitise.cu: flags, ordered compaction, bounding box and
+        affine map in binary64 on the device); the result is identical to the host path (same binary64 arithmetic).
         """
+        if device is not None:
+            return self._sanitised_on_device(drop_zero_length, normalise, return_map, torch.device(device))
         kept = [i for i, o in enumerate(self.objects)
                 if not (drop_zero_length and isinstance(o, Wall) and not np.any(o.xys[1] != o.xys[0]))]
         objs = [self.objects[i] for i in kept]
@@ -186,6 +192,53 @@ class Scene:
         sc = Scene(tx, rx, objs)
         if return_map:
             return sc, {"kept": kept, "origin": origin.astype(np.float64), "scale": scale}
+        return sc
+
+    def _sanitised_on_device(self, drop_zero_length, normalise, return_map, device):
+        import ctypes as C
+
+        F._require_cuda(device)
+        lib = F.L.lib()
+        xys, kinds, phis = self.packed_objects()
+        n = xys.shape[0]
+        names = list(self.transmitters) + list(self.receivers)
+        pts = np.stack([p.xy for p in (*self.transmitters.values(), *self.receivers.values())]) if names \
+            else np.zeros((0, 2), np.float32)
+        with torch.cuda.device(device):
+            d_xys = torch.as_tensor(xys).to(device).contiguous()
+            d_kinds, d_phis = torch.as_tensor(kinds).to(device), torch.as_tensor(phis).to(device)
+            d_pts = torch.as_tensor(pts).to(device).contiguous()
+            o_xys, o_kinds, o_phis = torch.empty_like(d_xys), torch.empty_like(d_kinds), torch.empty_like(d_phis)
+            kept = torch.empty(max(n, 1), dtype=torch.int32, device=device)
+            n_kept = torch.zeros(1, dtype=torch.int32, device=device)
+            affine = torch.zeros(3, dtype=torch.float64, device=device)
+            o_pts = torch.empty_like(d_pts)
+            st = torch.cuda.current_stream(device).cuda_stream
+            ptr = lambda t: t.data_ptr() if t.numel() else None  # noqa: E731
+            F.L.check(lib.d2d_sanitise_scene(ptr(d_xys), ptr(d_kinds), ptr(d_phis), n, ptr(d_pts), pts.shape[0],
+                                             int(bool(drop_zero_length)), int(bool(normalise)), ptr(o_xys), ptr(o_kinds),
+                                             ptr(o_phis), kept.data_ptr(), n_kept.data_ptr(), None, affine.data_ptr(), st),
+                      "d2d_sanitise_scene")
+            F.L.check(lib.d2d_affine_points(ptr(d_pts), pts.shape[0], affine.data_ptr(), ptr(o_pts), st), "d2d_affine_points")
+            m = int(n_kept.item())
+            kept_h = kept[:m].cpu().numpy().tolist()
+            xys_h, kinds_h, phis_h = o_xys[:m].cpu().numpy(), o_kinds[:m].cpu().numpy(), o_phis[:m].cpu().numpy()
+            aff = affine.cpu().numpy()
+            pts_h = o_pts.cpu().numpy()
+        objs = []
+        for q in range(m):
+            if kinds_h[q] == Vertex.KIND:
+                objs.append(Vertex(xy=xys_h[q, 0]))
+            elif kinds_h[q] == RIS.KIND:
+                objs.append(RIS(xys=xys_h[q], phi=float(phis_h[q])))
+            else:
+                objs.append(Wall(xys=xys_h[q]))
+        nt = len(self.transmitters)
+        tx = {k: Point(xy=pts_h[i]) for i, k in enumerate(self.transmitters)}
+        rx = {k: Point(xy=pts_h[nt + i]) for i, k in enumerate(self.receivers)}
+        sc = Scene(tx, rx, objs)
+        if return_map:
+            return sc, {"kept": kept_h, "origin": aff[:2].astype(np.float64), "scale": float(aff[2])}
         return sc
 
     # ---- Plottable pieces needed to build inputs (abc.py:30-126, scene.py:1023-1036) --------------

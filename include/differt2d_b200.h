@@ -194,6 +194,28 @@ int d2d_paths(const D2DProblem *p, float min_valid, int32_t emit_all, D2DPathRec
               unsigned long long *count, void *stream);
 
 /*
+ * Scene sanitiser on the device.  Scene.from_geojson (scene.py:628-663) emits one ZERO-LENGTH closure wall
+ * per closed polygon ring (coords[i-1] wraps to the duplicated vertex): every candidate through it is invalid, and the
+ * reference's own reverse mode turns NaN for the whole map (geometry.py:1105); raw lon/lat coordinates add ~3 % of a wall
+ * length of fp32 lattice noise to every parametric coordinate.  This call builds the object table a well-conditioned
+ * trace wants.  With drop_zero_length == 0 and normalise == 0 it copies the scene unchanged (the PARITY switch: results on
+ * a sanitised scene differ from the reference's on the raw one, which stays the parity case).
+ *   flags      [n] u8 or NULL: 1 for a zero-length Wall / RIS (a Vertex is never flagged)
+ *   xys_out    [n,2,2]; kinds_out [n] / phis_out [n] / kept_index [n] i32 or NULL: the kept objects, compacted, order kept;
+ *              kept_index[q] = index of kept object q in the input (to carry cotangents back); *n_kept (device i32)
+ *   points     [n_points,2] or NULL: transmitters / receivers taking part in the bounding box (scene.py:1023-1036)
+ *   affine     [3] device doubles {origin x, origin y, scale}: x' = (x - origin) / scale, computed AND applied in binary64,
+ *              rounded once to binary32 ({0, 0, 1} without normalise); d/d raw = d/d sanitised / scale
+ * n <= D2D_MAX_OBJECTS.  d2d_affine_points applies the same map to any point set (transmitters, receivers, a grid).
+ */
+int d2d_sanitise_scene(const float *xys, const uint8_t *kinds, const float *phis, int32_t n, const float *points,
+                       int64_t n_points, int32_t drop_zero_length, int32_t normalise, float *xys_out,
+                       uint8_t *kinds_out, float *phis_out, int32_t *kept_index, int32_t *n_kept, uint8_t *flags,
+                       double *affine, void *stream);
+int d2d_affine_points(const float *points, int64_t n_points, const double *affine /*device*/, float *points_out,
+                      void *stream);
+
+/*
  * Host-buffer entry (numpy users of the reference; `bench.py`'s end-to-end leg): every pointer of `p` and every
  * output is a HOST pointer (pinned memory lets the copies overlap); the call stages the inputs, runs the forward
  * kernel and — when any *_bar output is non-NULL — the backward kernel over the activity mask, copies the results

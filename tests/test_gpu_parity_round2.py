@@ -569,3 +569,34 @@ def test_solver_steps100_distance_is_within_the_oracles_own_fp32_noise(method, m
         report.append(f"{k}: kernel-vs-fp32 {d_kernel:.2e}, fp32-vs-fp64 {d_oracle:.2e}")
         assert d_kernel <= 4.0 * d_oracle + 1e-4, f"{method} {mode} {k}: {report[-1]}"
     print(f"[parity] {method} {mode} steps=100: " + "; ".join(report))
+
+
+def test_scene_sanitiser_on_the_device():
+    """d2d_sanitise_scene / d2d_affine_points (csrc/d2d_sanitise.cu) against the host path of
+    Scene.sanitised (same binary64 arithmetic: identical tables), the parity switch (nothing dropped, nothing moved:
+    the scene comes back unchanged), and a mixed scene (a Vertex is never flagged, a RIS keeps its angle)."""
+    raw = SCENES["geojson"]
+    for drop, norm in ((True, False), (False, True), (True, True), (False, False)):
+        host, hm = raw.sanitised(drop_zero_length=drop, normalise=norm, return_map=True)
+        dev, dm = raw.sanitised(drop_zero_length=drop, normalise=norm, return_map=True, device="cuda")
+        assert dm["kept"] == hm["kept"] and len(dev.objects) == (26 if drop else 28)
+        assert np.array_equal(dm["origin"], hm["origin"]) and dm["scale"] == hm["scale"]
+        assert np.array_equal(dev.packed_objects()[0], host.packed_objects()[0])
+        for k in raw.transmitters:
+            assert np.array_equal(dev.transmitters[k].xy, host.transmitters[k].xy)
+        for k in raw.receivers:
+            assert np.array_equal(dev.receivers[k].xy, host.receivers[k].xy)
+        if not drop and not norm:
+            assert np.array_equal(dev.packed_objects()[0], raw.packed_objects()[0])
+    mixed = d.Scene.square_scene().add_objects(d.Vertex(xy=[0.3, 0.4]), d.RIS(xys=[[0.5, 0.3], [0.5, 0.7]], phi=0.6),
+                                                d.Wall(xys=[[0.2, 0.2], [0.2, 0.2]]))
+    dev, dm = mixed.sanitised(return_map=True, device="cuda")
+    assert dm["kept"] == [0, 1, 2, 3, 4, 5] and isinstance(dev.objects[4], d.Vertex) and isinstance(dev.objects[5], d.RIS)
+    assert abs(dev.objects[5].phi - 0.6) < 1e-6
+    # the sanitised scene traces without the NaN-poisoning closure walls and gives the same map: they never carry a path
+    # (residual |i_hat|^2 = 1 > tol) unless the receiver coincides with the transmitter — the bbox grid's NW corner —
+    # where both directions vanish; hence a grid strictly inside the box
+    X, Y = H.jittered_grid(raw, 32, 40, seed=4)
+    Za = raw.accumulate_on_receivers_grid_over_paths(X, Y, reduce_all=True, max_order=1, approx=False)
+    Zb = raw.sanitised(device="cuda").accumulate_on_receivers_grid_over_paths(X, Y, reduce_all=True, max_order=1, approx=False)
+    assert np.array_equal(Za, Zb)
