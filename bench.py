@@ -317,6 +317,29 @@ def _emit(line: dict) -> None:
 _REAL_STDOUT = None
 
 
+def _shutdown(D, torch, dev, graphs=()) -> None:
+    """Leaves the process group without ever hanging the launcher: CUDA graphs that captured NCCL kernels are released
+    FIRST (destroying a communicator that live graphs still reference blocked for the whole time limit on a 2-GPU
+    run), and a watchdog ends the process if the teardown itself does not return."""
+    import threading
+
+    for g in graphs:
+        try:
+            if g is not None:
+                g.reset()
+        except Exception:  # noqa: BLE001
+            pass
+    try:
+        torch.cuda.synchronize(dev)
+    except Exception:  # noqa: BLE001
+        pass
+    sys.stdout.flush()
+    sys.stderr.flush()
+    threading.Timer(30.0, lambda: os._exit(0)).start()  # (daemon-like: only fires if destroy_process_group blocks)
+    D.shutdown()
+    os._exit(0)  # the JSON line is out (rank 0) and every rank has left the group: nothing else to run
+
+
 def _quiet_stdout() -> None:
     global _REAL_STDOUT
     if _REAL_STDOUT is None:
@@ -705,6 +728,7 @@ def main() -> None:
     e2e_equal = bool(np.array_equal(Z_p.numpy(), job.Z.cpu().numpy()))
 
     extras = {}
+    graphs = [job.graph]
     if not args.no_extras:
         # strong-scaling leg (BASELINE config 3: 2048 x 2048 in total), every rank takes part
         if args.scaling == "weak":
@@ -713,6 +737,7 @@ def main() -> None:
                 sjob.step_eager(flush)
             if not args.no_graph:
                 sjob.capture(flush)
+                graphs.append(sjob.graph)
             s_ms = sjob.timed(flush, min(args.steps, 10), 3, barrier)
             extras["strong"] = {
                 "grid_global": list(GRID_STRONG), "n_gpus": world, "ms_per_step": s_ms,
@@ -731,7 +756,7 @@ def main() -> None:
 
     if rank != 0:
         if dist is not None:
-            D.shutdown()
+            _shutdown(D, torch, dev, graphs)
         return
 
     paths_step = float(n_rows) * n_cols * T * job.n_cand  # whole job, all ranks
@@ -819,7 +844,7 @@ def main() -> None:
         line["cpu_baseline"] = cpu_baseline_sample(args)
     _emit(line)
     if dist is not None:
-        D.shutdown()
+        _shutdown(D, torch, dev, graphs)
 
 
 def bench_p2p500(args, torch, L, F, D, dev, world, rank, dist) -> None:
@@ -874,7 +899,7 @@ def bench_p2p500(args, torch, L, F, D, dev, world, rank, dist) -> None:
                                       f"{int(buf.numel())} floats per step"},
                "checksum": {"Z": [float(v) for v in buf[:2].cpu()]}})
     if dist is not None:
-        D.shutdown()
+        _shutdown(D, torch, dev)
 
 
 if __name__ == "__main__":

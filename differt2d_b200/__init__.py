@@ -3,7 +3,7 @@ differt2d_b200 — B200-native (sm_100a CUDA) implementation of DiffeRT2d's rece
 path-tracing hot path, behind the reference's own Python API names.  See DESIGN.md.
 """
 
-from . import functional, logic, utils  # noqa: F401
+from . import functional, logic, optimizers, utils  # noqa: F401
 from ._lib import D2DError  # noqa: F401
 from .defaults import DEFAULT_ALPHA, DEFAULT_HEIGHT, DEFAULT_PATCH, DEFAULT_R_COEF  # noqa: F401
 from .functional import TraceConfig, power_bwd, power_fwd, power_map  # noqa: F401

@@ -23,6 +23,7 @@ METHOD_IMAGE, METHOD_FERMAT, METHOD_MINPATH = 0, 1, 2
 MODE_HARD, MODE_HARD_SIGMOID, MODE_SIGMOID = 0, 1, 2
 GRAD_CLEAN, GRAD_NAN_PARITY = 0, 1
 FUN_RECEIVED_POWER, FUN_LENGTH_SQUARED = 0, 1
+OPT_ADAM, OPT_SGD, OPT_NEWTON = 0, 1, 2
 
 
 class D2DError(RuntimeError):
@@ -64,6 +65,10 @@ class D2DProblem(C.Structure):
         ("active_mask", C.c_void_p),
         ("cand_shard_index", C.c_int32),
         ("cand_shard_count", C.c_int32),
+        ("optimizer", C.c_int32),
+        ("opt_b1", C.c_float),
+        ("opt_b2", C.c_float),
+        ("opt_eps", C.c_float),
         ("many", C.c_int32),
     ]
 

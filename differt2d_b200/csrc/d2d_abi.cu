@@ -126,6 +126,9 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
         return fail(D2D_ERR_INVALID_ARGUMENT, "alpha must be > 0 (activations must be non-decreasing)");
     if (p->method != D2D_METHOD_IMAGE && p->steps < 1)
         return fail(D2D_ERR_INVALID_ARGUMENT, "steps must be >= 1 (optimize.py:96 indexes losses[-1])");
+    if (p->optimizer < D2D_OPT_ADAM || p->optimizer > D2D_OPT_NEWTON) return fail(D2D_ERR_INVALID_ARGUMENT, "bad optimizer");
+    if (p->optimizer == D2D_OPT_NEWTON && p->many > 1)
+        return fail(D2D_ERR_UNSUPPORTED, "D2D_OPT_NEWTON does not support restarts (many > 1)");
     if (p->grad_mode != D2D_GRAD_CLEAN && p->grad_mode != D2D_GRAD_NAN_PARITY)
         return fail(D2D_ERR_INVALID_ARGUMENT, "bad grad_mode");
     if (p->grad_mode == D2D_GRAD_NAN_PARITY && p->method != D2D_METHOD_IMAGE)
@@ -153,6 +156,10 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
     k.tol = p->tol;
     k.patch = p->patch;
     k.lr = p->lr;
+    k.opt = p->optimizer;
+    k.b1 = p->opt_b1;
+    k.b2 = p->opt_b2;
+    k.opt_eps = p->opt_eps;
     // utils.py:52-54 — Python folds r_coef**n and height*height in double, JAX then casts to f32
     k.h2 = (float)(p->height * p->height);
     for (int i = 0; i <= d2d::kMaxOrder; ++i) k.rc_pow[i] = (float)std::pow(p->r_coef, (double)i);
@@ -212,6 +219,10 @@ void d2d_problem_defaults(D2DProblem* p) {
     p->method = D2D_METHOD_IMAGE;
     p->steps = 100;  // optimize.py:49
     p->lr = 0.1f;    // optimize.py:83
+    p->optimizer = D2D_OPT_ADAM;
+    p->opt_b1 = 0.9f;  // optax.adam defaults
+    p->opt_b2 = 0.999f;
+    p->opt_eps = 1e-8f;
     p->mode = D2D_MODE_HARD;
     p->alpha = 100.0f;  // defaults.py:3
     p->tol = 1e-2f;     // geometry.py:915

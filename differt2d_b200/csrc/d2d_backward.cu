@@ -15,6 +15,7 @@
 #include "d2d_launch.h"
 #include "d2d_solver.cuh"
 #include "d2d_solver_adj.cuh"
+#include "d2d_newton.cuh"
 
 namespace d2d {
 
@@ -47,8 +48,13 @@ __device__ __noinline__ float path_vjp(const SceneTab& T, const KParams& p, cons
     float solver_loss = 0.f;
     const int stride = adam_ckpt_stride(p.steps);
     if constexpr (kSolver) {
-        const int restart = p.many > 1 ? best_restart<METHOD, K>(T, p, cd, tx, rx, col) : 0;
-        solver_loss = adam_scan_ckpt<METHOD, K>(T, p, cd, tx, rx, col, restart, stride, ck, th_final);
+        if (p.opt == D2D_OPT_NEWTON) {  // the forward's Newton iterations again; differentiated implicitly below
+            adam_init<K>(T, p, cd, col, 0, th_final);
+            solver_loss = newton_solve<METHOD, K>(T, p, cd, tx, rx, th_final.th);
+        } else {
+            const int restart = p.many > 1 ? best_restart<METHOD, K>(T, p, cd, tx, rx, col) : 0;
+            solver_loss = adam_scan_ckpt<METHOD, K>(T, p, cd, tx, rx, col, restart, stride, ck, th_final);
+        }
         place_points<K>(T, cd, th_final.th, X);
     } else {
 #pragma unroll
@@ -250,7 +256,10 @@ __device__ __noinline__ float path_vjp(const SceneTab& T, const KParams& p, cons
         }
         tx_bar = Xb[0];
         rx_bar = Xb[K + 1];
-        adam_scan_reverse<METHOD, K>(T, p, cd, tx, rx, stride, ck, thb, solver_loss_bar, tx_bar, rx_bar, oa);
+        if (p.opt == D2D_OPT_NEWTON)
+            newton_reverse<METHOD, K>(T, cd, th_final.th, tx, rx, thb, solver_loss_bar, tx_bar, rx_bar, oa);
+        else
+            adam_scan_reverse<METHOD, K>(T, p, cd, tx, rx, stride, ck, thb, solver_loss_bar, tx_bar, rx_bar, oa);
         return contrib;
     }
     // (3) backward scan of the image method : geometry.py:1093-1107 (clean `where`)

@@ -64,6 +64,8 @@ struct KParams {
     int min_order, max_order;
     int steps;
     int many;              // restarts of the Fermat/MinPath scan (>= 1)
+    int opt;               // D2D_OPT_*
+    float b1, b2, opt_eps; // Adam b1 / b2 / eps; SGD momentum in b1
     int fun, reduce_all;
     long long C_total;     // candidates over all orders (columns of valid_out)
     float alpha, tol, patch, lr;

@@ -46,7 +46,11 @@ constexpr int kBlock = 128;
 #define D2D_FWD_MIN_CTAS 8
 #endif
 #ifndef D2D_BWD_MIN_CTAS
-#define D2D_BWD_MIN_CTAS 5
+#if defined(D2D_TU_SOLVER) && D2D_TU_SOLVER
+#define D2D_BWD_MIN_CTAS 5  // FermatPath / MinPath: the reverse sweep through the scan keeps far more state alive
+#else
+#define D2D_BWD_MIN_CTAS 8  // ImagePath: 64 registers; measured 8 > 6 > 5 > 4 > 3 CTAs/SM on both bench legs (r02g, r02j)
+#endif
 #endif
 constexpr int kTileCols = 16;
 constexpr int kTileRows = 8;

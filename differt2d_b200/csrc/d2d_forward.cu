@@ -9,6 +9,7 @@
 #include "d2d_driver.cuh"
 #include "d2d_launch.h"
 #include "d2d_solver.cuh"
+#include "d2d_newton.cuh"
 
 namespace d2d {
 

@@ -54,6 +54,27 @@ __device__ __forceinline__ float solver_loss_grad(const SceneTab& T, const Cand<
     return loss;
 }
 
+// D2D_OPT_NEWTON (d2d_newton.cuh, included by every kernel translation unit after this header): damped Newton
+// iterations from th (in / out); returns the loss at the returned point.
+template <int METHOD, int K>
+__device__ float newton_solve(const SceneTab& T, const KParams& p, const Cand<K>& cd, const float2 tx, const float2 rx,
+                              float (&th)[K > 0 ? K : 1]);
+
+// One optimiser update of unknown i for the loss gradient g (optimize.py:87-93 with the optimizer of p.opt):
+// optax.adam: mu, nu moments, bias correction with b1^s / b2^s (bc1, bc2); optax.sgd: mu is the momentum trace.
+__device__ __forceinline__ void optimizer_update(const KParams& p, const float g, const float bc1, const float bc2,
+                                                 float& th, float& mu, float& nu) {
+    if (p.opt == D2D_OPT_SGD) {
+        mu = g + p.b1 * mu;  // optax.trace(decay = momentum)
+        th = th + (-p.lr) * mu;
+        return;
+    }
+    mu = (1.0f - p.b1) * g + p.b1 * mu;
+    nu = (1.0f - p.b2) * (g * g) + p.b2 * nu;
+    const float mh = mu / bc1, nh = nu / bc2;
+    th = th + (-p.lr) * (mh / (sqrtf(nh) + p.opt_eps));
+}
+
 template <int METHOD, int K>
 __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams& p, const Cand<K>& cd,
                                                const float2 tx, const float2 rx, const long long col,
@@ -71,7 +92,7 @@ __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams&
     float best = 0.0f, last = 0.0f;
     X[0] = tx;
     X[K + 1] = rx;
-    const float b1 = 0.9f, b2 = 0.999f, eps = 1e-8f;  // optax.adam defaults
+    const float b1 = p.b1, b2 = p.b2;  // optax.adam defaults 0.9 / 0.999 / 1e-8 unless the caller chose otherwise
     // minimize_many_random_uniform (optimize.py:142-182): `many` independent scans, keep argmin of the final losses
     for (int r = 0; r < p.many; ++r) {
         int u = 0;
@@ -84,6 +105,10 @@ __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams&
                 th[i] = p.x0 ? p.x0[(col * p.many + r) * p.max_order + u] : 0.5f;
                 ++u;
             }
+        }
+        if (p.opt == D2D_OPT_NEWTON) {
+            last = newton_solve<METHOD, K>(T, p, cd, tx, rx, th);
+            break;  // (no restarts in this mode)
         }
         float b1p = 1.0f, b2p = 1.0f;
         for (int s = 0; s < p.steps; ++s) {
@@ -98,10 +123,7 @@ __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams&
                 if (T.kind[cd.c[i]] == D2D_KIND_VERTEX) continue;
                 const float4 w0 = T.w0[cd.c[i]];
                 const float g = G[i + 1].x * w0.z + G[i + 1].y * w0.w;
-                mu[i] = (1.0f - b1) * g + b1 * mu[i];
-                nu[i] = (1.0f - b2) * (g * g) + b2 * nu[i];
-                const float mh = mu[i] / bc1, nh = nu[i] / bc2;
-                th[i] = th[i] + (-p.lr) * (mh / (sqrtf(nh) + eps));
+                optimizer_update(p, g, bc1, bc2, th[i], mu[i], nu[i]);
             }
         }
         if (p.many == 1) break;
@@ -121,7 +143,7 @@ __device__ __forceinline__ void construct_path(const SceneTab& T, const KParams&
     if (METHOD == D2D_METHOD_FERMAT) {
         // geometry.py:1202-1204: loss = path_loss(xys), left to validity()
     } else {
-        if (p.steps <= 0) {
+        if (p.steps <= 0 && p.opt != D2D_OPT_NEWTON) {
             float2 G[K + 2];
             last = solver_loss_grad<METHOD, K>(T, cd, X, G);
         }

@@ -202,7 +202,6 @@ struct AdamState {
     float b1p, b2p;
 };
 
-constexpr float kB1 = 0.9f, kB2 = 0.999f, kAdamEps = 1e-8f;  // optax.adam defaults (optimize.py:83)
 
 // One iteration of optimize.py:87-93, identical (bit for bit) to the loop of construct_path (d2d_solver.cuh).
 // Returns the loss at the iterate BEFORE the update.
@@ -214,18 +213,15 @@ __device__ __forceinline__ float adam_step(const SceneTab& T, const KParams& p, 
     X[K + 1] = rx;
     place_points<K>(T, cd, st.th, X);
     const float loss = solver_loss_grad<METHOD, K>(T, cd, X, G);
-    st.b1p *= kB1;
-    st.b2p *= kB2;
+    st.b1p *= p.b1;
+    st.b2p *= p.b2;
     const float bc1 = 1.0f - st.b1p, bc2 = 1.0f - st.b2p;
 #pragma unroll
     for (int i = 0; i < K; ++i) {
         if (T.kind[cd.c[i]] == D2D_KIND_VERTEX) continue;
         const float4 w0 = T.w0[cd.c[i]];
         const float g = G[i + 1].x * w0.z + G[i + 1].y * w0.w;
-        st.mu[i] = (1.0f - kB1) * g + kB1 * st.mu[i];
-        st.nu[i] = (1.0f - kB2) * (g * g) + kB2 * st.nu[i];
-        const float mh = st.mu[i] / bc1, nh = st.nu[i] / bc2;
-        st.th[i] = st.th[i] + (-p.lr) * (mh / (sqrtf(nh) + kAdamEps));
+        optimizer_update(p, g, bc1, bc2, st.th[i], st.mu[i], st.nu[i]);
     }
     return loss;
 }
@@ -326,7 +322,7 @@ __device__ __forceinline__ void adam_scan_reverse(const SceneTab& T, const KPara
                 X[K + 1] = rx;
                 place_points<K>(T, cd, pre.th, X);
                 solver_loss_grad<METHOD, K>(T, cd, X, G);
-                const float bc1 = 1.0f - pre.b1p * kB1, bc2 = 1.0f - pre.b2p * kB2;
+                const float bc1 = 1.0f - pre.b1p * p.b1, bc2 = 1.0f - pre.b2p * p.b2;
                 float lg[KK];
                 bool any = false;
 #pragma unroll
@@ -335,19 +331,26 @@ __device__ __forceinline__ void adam_scan_reverse(const SceneTab& T, const KPara
                     if (T.kind[cd.c[i]] == D2D_KIND_VERTEX) continue;
                     const float4 w0 = T.w0[cd.c[i]];
                     const float g = G[i + 1].x * w0.z + G[i + 1].y * w0.w;
-                    const float mu = (1.0f - kB1) * g + kB1 * pre.mu[i];
-                    const float nu = (1.0f - kB2) * (g * g) + kB2 * pre.nu[i];
+                    if (p.opt == D2D_OPT_SGD) {  // trace' = g + m trace ; theta' = theta - lr trace'
+                        const float ltr_s = lmu[i] + (-p.lr) * lth[i];
+                        lg[i] = ltr_s;
+                        lmu[i] = p.b1 * ltr_s;
+                        any = any || lg[i] != 0.f;
+                        continue;
+                    }
+                    const float mu = (1.0f - p.b1) * g + p.b1 * pre.mu[i];
+                    const float nu = (1.0f - p.b2) * (g * g) + p.b2 * pre.nu[i];
                     const float mh = mu / bc1, nh = nu / bc2;
-                    const float sq = sqrtf(nh), den = sq + kAdamEps;
+                    const float sq = sqrtf(nh), den = sq + p.opt_eps;
                     const float lupd = -p.lr * lth[i];
                     const float lmh = lupd / den;
                     const float lden = -lupd * mh / (den * den);
                     const float lnh = sq > 0.f ? 0.5f * lden / sq : 0.f;  // clean: d sqrt(0) is a masked constant
                     const float lmu_s = lmu[i] + lmh / bc1;
                     const float lnu_s = lnu[i] + lnh / bc2;
-                    lg[i] = (1.0f - kB1) * lmu_s + (1.0f - kB2) * 2.0f * g * lnu_s;
-                    lmu[i] = kB1 * lmu_s;
-                    lnu[i] = kB2 * lnu_s;
+                    lg[i] = (1.0f - p.b1) * lmu_s + (1.0f - p.b2) * 2.0f * g * lnu_s;
+                    lmu[i] = p.b1 * lmu_s;
+                    lnu[i] = p.b2 * lnu_s;
                     any = any || lg[i] != 0.f;
                 }
                 if (METHOD == D2D_METHOD_MINPATH && s == S - 1 && loss_bar != 0.f) {

@@ -21,6 +21,7 @@ METHODS = {"image": L.METHOD_IMAGE, "fermat": L.METHOD_FERMAT, "minpath": L.METH
 FUNS = {"received_power": L.FUN_RECEIVED_POWER, "length_squared": L.FUN_LENGTH_SQUARED}
 ROLES = {"receivers": L.GRID_RECEIVERS, "transmitters": L.GRID_TRANSMITTERS}
 GRAD_MODES = {"clean": L.GRAD_CLEAN, "nan_parity": L.GRAD_NAN_PARITY}
+OPTIMIZERS = {"adam": L.OPT_ADAM, "sgd": L.OPT_SGD, "newton": L.OPT_NEWTON}
 
 
 @dataclass(frozen=True)
@@ -35,6 +36,13 @@ class TraceConfig:
     steps: int = 100
     many: int = 1  # Fermat/MinPath restarts (optimize.py:142-182); x0 is then [C, many, max_order]
     lr: float = 0.1
+    # optimize.minimize(..., optimizer=...) (optimize.py:44-97): "adam" = optax.adam(lr, b1, b2, eps) (the reference's
+    # default), "sgd" = optax.sgd(lr, momentum = opt_b1), "newton" = damped Newton iterations + implicit reverse mode
+    # (a non-parity fast mode, csrc/d2d_newton.cuh); see differt2d_b200.optimizers
+    optimizer: str = "adam"
+    opt_b1: float = 0.9
+    opt_b2: float = 0.999
+    opt_eps: float = 1e-8
     mode: str = "hard"
     tol: float = 1e-2
     patch: float = DEFAULT_PATCH
@@ -110,6 +118,7 @@ class _Packed:
         p.steps = int(cfg.steps)
         p.many = int(cfg.many)
         p.lr = float(cfg.lr)
+        p.optimizer, p.opt_b1, p.opt_b2, p.opt_eps = OPTIMIZERS[cfg.optimizer], float(cfg.opt_b1), float(cfg.opt_b2), float(cfg.opt_eps)
         p.x0 = self.x0.data_ptr() if self.x0 is not None else None
         p.mode = MODES[cfg.mode]
         p.alpha = alpha_f
@@ -248,6 +257,7 @@ def power_host(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phi
     p.min_order, p.max_order = int(cfg.min_order), int(cfg.max_order)
     p.filter_nodes, p.n_filter = (flt.ctypes.data if flt.size else None), int(flt.size)
     p.method, p.steps, p.many, p.lr = METHODS[cfg.method], int(cfg.steps), int(cfg.many), float(cfg.lr)
+    p.optimizer, p.opt_b1, p.opt_b2, p.opt_eps = OPTIMIZERS[cfg.optimizer], float(cfg.opt_b1), float(cfg.opt_b2), float(cfg.opt_eps)
     p.x0 = x0_h.ctypes.data if x0_h is not None else None
     p.mode, p.alpha, p.tol, p.patch = MODES[cfg.mode], float(alpha), float(cfg.tol), float(cfg.patch)
     p.fun, p.r_coef, p.height = FUNS[cfg.fun], float(cfg.r_coef), float(cfg.height)

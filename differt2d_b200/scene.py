@@ -21,7 +21,7 @@ import numpy as np
 import torch
 
 from . import functional as F
-from . import utils
+from . import optimizers, utils
 from .defaults import DEFAULT_ALPHA, DEFAULT_HEIGHT, DEFAULT_PATCH, DEFAULT_R_COEF
 from .geometry import RIS, FermatPath, ImagePath, MinPath, ObjectBatch, Path, PathBatch, Point, PointBatch, Vertex, Wall
 from .logic import resolve_mode
@@ -323,8 +323,13 @@ class Scene:
         if many < 1:
             raise ValueError("many must be >= 1")
         optimizer = pk.pop("optimizer", None)
-        if optimizer is not None or pk:
-            raise NotImplementedError(f"unsupported path_cls_kwargs: {sorted(pk) + (['optimizer'] if optimizer else [])}")
+        if optimizer is None:
+            optimizer = optimizers.adam()  # optimize.py:83
+        if not isinstance(optimizer, optimizers.Optimizer):
+            raise NotImplementedError("the solver runs inside the CUDA kernels: `optimizer` must be one of "
+                                      "differt2d_b200.optimizers.adam / sgd / newton (an optax object cannot be fused)")
+        if pk:
+            raise NotImplementedError(f"unsupported path_cls_kwargs: {sorted(pk)}")
         mode = resolve_mode(kwargs.pop("approx", None), kwargs.pop("function", None))
         alpha = kwargs.pop("alpha", DEFAULT_ALPHA)
         tol = float(kwargs.pop("tol", 1e-2))
@@ -340,7 +345,8 @@ class Scene:
             raise TypeError("ImagePath cannot interact with Vertex objects (geometry.py:1020 expects walls)")
         cfg = F.TraceConfig(grid_role=grid_role, min_order=min_order, max_order=max_order,
                             filter_nodes=self._filter_nodes(filter_objects), method=method, steps=steps, many=many,
-                            lr=0.1, mode=mode, tol=tol, patch=patch, fun="received_power" if fname == "generic" else fname,
+                            lr=optimizer.learning_rate, optimizer=optimizer.kind, opt_b1=optimizer.b1,
+                            opt_b2=optimizer.b2, opt_eps=optimizer.eps, mode=mode, tol=tol, patch=patch, fun="received_power" if fname == "generic" else fname,
                             r_coef=r_coef, height=height, reduce_all=bool(reduce_all),
                             grad_mode="nan_parity" if nan_parity else "clean")
         return cfg, alpha, fname == "generic"

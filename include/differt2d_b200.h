@@ -62,6 +62,13 @@ extern "C" {
                               /* inf): ImagePath only, every candidate visited without culling (diagnostic mode;       */
                               /* csrc/d2d_nan.cu)                                                                      */
 
+/* the optimiser behind FermatPath / MinPath — optimize.minimize(..., optimizer=...) (optimize.py:44-97) */
+#define D2D_OPT_ADAM 0   /* optax.adam(lr, b1 = opt_b1, b2 = opt_b2, eps = opt_eps): the reference's default (optimize.py:83) */
+#define D2D_OPT_SGD 1    /* optax.sgd(lr, momentum = opt_b1) (0 = plain gradient descent)                                    */
+#define D2D_OPT_NEWTON 2 /* NOT a reference optimiser — a fast mode: damped Newton iterations on the same loss (`steps` of   */
+                         /* them, 8-12 suffice); the reverse mode differentiates the CONVERGED point implicitly               */
+                         /* (d theta / d q = -H^-1 d grad / d q) instead of unrolling the scan; many > 1 is not supported      */
+
 #define D2D_OK 0
 #define D2D_ERR_INVALID_ARGUMENT 1
 #define D2D_ERR_UNSUPPORTED 2
@@ -123,6 +130,10 @@ typedef struct D2DProblem {
                               /* round robin: equal work per rank); order 0 belongs to shard 0.  Z and every cotangent  */
                               /* are then PARTIAL sums: the caller adds them over the shards (one all-reduce).           */
                               /* 0 or 1 = the whole list.                                                                */
+    int32_t optimizer;  /* D2D_OPT_*                                                                  */
+    float opt_b1;       /* Adam b1 (0.9) / SGD momentum                                               */
+    float opt_b2;       /* Adam b2 (0.999)                                                            */
+    float opt_eps;      /* Adam eps (1e-8)                                                            */
     int32_t many; /* Fermat/MinPath restarts, optimize.py:142-182 (minimize_many_random_uniform): the scan runs    */
                   /* `many` times from x0[c, 0..many-1] and the iterate with the smallest final loss is kept       */
                   /* (first one on ties, jnp.argmin).  0 or 1 = a single run (the path classes' default, :1198).   */

@@ -514,6 +514,26 @@ def _stack_pts(pts):
     return torch.stack([p.expand(shape) for p in pts], dim=-2)
 
 
+OPTIMIZER = ("adam", 0.9, 0.999, 1e-8)  # (kind, b1 | momentum, b2, eps): see `optimizer`
+
+
+class optimizer:
+    """``with optimizer("sgd", momentum=0.5):`` — the optax transformation behind optimize.minimize (optimize.py:44-97):
+    "adam" = optax.adam(lr, b1, b2, eps), "sgd" = optax.sgd(lr, momentum) (optax.trace(decay=momentum) then scale(-lr))."""
+
+    def __init__(self, kind="adam", b1=0.9, b2=0.999, eps=1e-8, momentum=None):
+        self.val = (kind, float(momentum or 0.0) if kind == "sgd" else float(b1), float(b2), float(eps))
+
+    def __enter__(self):
+        global OPTIMIZER
+        self.prev = OPTIMIZER
+        OPTIMIZER = self.val
+
+    def __exit__(self, *a):
+        global OPTIMIZER
+        OPTIMIZER = self.prev
+
+
 def minimize_adam(fun, x0, steps=100, lr=0.1, differentiable=False):
     """
     optimize.py:44-97 with optax.adam(0.1) (optax 0.2.4: scale_by_adam b1=.9 b2=.999 eps=1e-8
@@ -521,7 +541,7 @@ def minimize_adam(fun, x0, steps=100, lr=0.1, differentiable=False):
     ``fun`` maps theta [..., n] -> loss [...]; elements are independent (vmap semantics).
     Returns (x_final, loss at the iterate BEFORE the last update) — optimize.py:96-97.
     """
-    b1, b2, eps = 0.9, 0.999, 1e-8
+    kind, b1, b2, eps = OPTIMIZER
     x = x0
     mu = torch.zeros_like(x0)
     nu = torch.zeros_like(x0)
@@ -541,6 +561,10 @@ def minimize_adam(fun, x0, steps=100, lr=0.1, differentiable=False):
                 (g,) = torch.autograd.grad(loss.sum(), xg)
             loss = loss.detach()
             x = xg.detach()
+        if kind == "sgd":  # optax.sgd: trace = g + momentum * trace ; update = -lr * trace
+            mu = g + b1 * mu
+            x = x + (-lr) * mu
+            continue
         mu = (1 - b1) * g + b1 * mu
         nu = (1 - b2) * (g * g) + b2 * nu
         bc1 = _NP(1) - _NP(b1) ** _NP(count)

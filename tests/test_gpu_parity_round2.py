@@ -600,3 +600,130 @@ def test_scene_sanitiser_on_the_device():
     Za = raw.accumulate_on_receivers_grid_over_paths(X, Y, reduce_all=True, max_order=1, approx=False)
     Zb = raw.sanitised(device="cuda").accumulate_on_receivers_grid_over_paths(X, Y, reduce_all=True, max_order=1, approx=False)
     assert np.array_equal(Za, Zb)
+
+
+# ---- optimisers of FermatPath / MinPath: optax.adam hyper-parameters, optax.sgd, Newton fast mode -------
+def _solver_case_with_optimizer(method, mode, steps, opt, oracle_opt, *, lr, n=5, m=6):
+    from tests.test_gpu_parity import _vertex_scene
+
+    sc = H.generic_position(_vertex_scene())
+    osc = H.oracle_scene_from_product(sc)
+    X, Y = H.jittered_grid(sc, n, m, seed=3)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, kinds, phis = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    x0 = np.random.default_rng(1234).random((50, 2), dtype=np.float32)
+    Zbar = (0.5 + np.random.default_rng(7).random(X.shape)).astype(np.float32)
+    cfg = _cfg(mode, max_order=2, method=method, steps=steps, grid_cols=m, reduce_all=True, lr=lr, **opt)
+    got = F.power_bwd(cfg, xys, fixed, grid, Zbar.reshape(-1), kinds=kinds, phis=phis, x0=x0, alpha=50.0, device="cuda")
+    with R.optimizer(**oracle_opt):
+        Zo, go = R.power_map_and_vjp(osc, X, Y, Zbar, method=method, max_order=2, x0=x0, steps=steps, lr=lr,
+                                     approx=mode != "hard", alpha=50.0, function="hard_sigmoid")
+    want = {"Z": Zo, "grid": go["grid"], "objects": go["xys"], "fixed": go["fixed"], "alpha": go["alpha"]}
+    err = {}
+    for k, w in want.items():
+        a = got[k].cpu().numpy().reshape(-1).astype(np.float64)
+        b = w.detach().numpy().reshape(-1).astype(np.float64)
+        err[k] = np.abs(a - b).max() / max(np.abs(b).max(), 1e-30) if np.abs(b).max() > 0 else np.abs(a).max()
+    return err
+
+
+@pytest.mark.parametrize("method", ["fermat", "minpath"])
+@pytest.mark.parametrize("name,opt,oracle_opt,lr", [
+    ("adam_hyper", dict(optimizer="adam", opt_b1=0.8, opt_b2=0.95, opt_eps=1e-6), dict(kind="adam", b1=0.8, b2=0.95, eps=1e-6), 0.05),
+    ("sgd", dict(optimizer="sgd", opt_b1=0.0), dict(kind="sgd", momentum=0.0), 0.02),
+    ("sgd_momentum", dict(optimizer="sgd", opt_b1=0.6), dict(kind="sgd", momentum=0.6), 0.01),
+])
+def test_solver_other_optimizers_vs_oracle(method, name, opt, oracle_opt, lr):
+    """optimize.minimize(..., optimizer=...) (optimize.py:44-97) with optax.adam's hyper-parameters changed and with
+    optax.sgd (plain and with momentum): forward map and the VJP through the scan against torch autograd over the
+    restated loop (short scans: 6 steps pin the algebra of every term, see test_solver_vjp_through_adam_scan)."""
+    err = _solver_case_with_optimizer(method, "hard_sigmoid", 6, opt, oracle_opt, lr=lr)
+    for k, e in err.items():
+        assert e < 2e-4, (name, k, e, err)
+
+
+@pytest.mark.parametrize("method", ["fermat", "minpath"])
+def test_newton_fast_mode_converges_to_the_image_path(method):
+    """D2D_OPT_NEWTON (csrc/d2d_newton.cuh; not a reference optimiser).  In a convex room (square_scene, generic
+    position) and with hard logic the stationary point of both losses that a valid path sits at is the specular path,
+    i.e. what ImagePath constructs in closed form (geometry.py:1017-1114).  (With smooth logic the iterative path
+    classes legitimately differ from ImagePath: a candidate that crosses a wall instead of reflecting has residual 4
+    under the image method and anything in [0, 4] at Fermat's crossing point; measured: 100 Adam steps reproduce 38-43 %
+    of the image-method map at alpha = 30, 72-84 % with hard logic.)  30 damped Newton iterations must reproduce the
+    image-method map on more receivers than 100 Adam steps (the reference's default) do, and put the vertices of the
+    valid paths closer to the image method's."""
+    sc = H.generic_position(SCENES["square"])
+    X, Y = H.jittered_grid(sc, 20, 22, seed=3)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    x0 = np.random.default_rng(5).random((17, 2), dtype=np.float32)
+    kw = dict(max_order=2, grid_cols=X.shape[1], reduce_all=True)
+    zi = F.power_fwd(_cfg("hard", **kw), xys, fixed, grid, device="cuda").cpu().numpy()
+    zn = F.power_fwd(_cfg("hard", method=method, optimizer="newton", steps=30, **kw), xys, fixed, grid, x0=x0,
+                     device="cuda").cpu().numpy()
+    za = F.power_fwd(_cfg("hard", method=method, steps=100, **kw), xys, fixed, grid, x0=x0, device="cuda").cpu().numpy()
+    close = lambda a: float(np.isclose(a, zi, rtol=1e-3, atol=1e-5 * np.abs(zi).max()).mean())  # noqa: E731
+    assert close(zn) > 0.93 and close(zn) > close(za), (close(zn), close(za))
+    sub = grid[::37]
+    pk = dict(max_order=2)
+    ri = F.paths(_cfg("hard", **pk), xys, fixed, sub, emit_all=True, device="cuda")
+    rn = F.paths(_cfg("hard", method=method, optimizer="newton", steps=30, **pk), xys, fixed, sub, x0=x0, emit_all=True,
+                 device="cuda")
+    ra = F.paths(_cfg("hard", method=method, steps=100, **pk), xys, fixed, sub, x0=x0, emit_all=True, device="cuda")
+    ok = (ri["valid"] > 0) & (rn["valid"] > 0) & (ra["valid"] > 0)
+    dn = (rn["xys"] - ri["xys"]).abs().reshape(ok.shape[0], -1).max(-1).values[ok]
+    da = (ra["xys"] - ri["xys"]).abs().reshape(ok.shape[0], -1).max(-1).values[ok]
+    assert float(dn.median()) < 1e-5 and float(dn.median()) < float(da.median()), (float(dn.median()), float(da.median()))
+
+
+def test_newton_implicit_reverse_mode_matches_a_converged_scan():
+    """Reverse mode of the Newton mode = implicit differentiation of the fixed point (d theta* = -H^-1 dg/dq dq): one
+    solve + one dual evaluation.  Yardstick: plain gradient descent (optax.sgd, whose unrolled reverse sweep is pinned
+    against the autograd oracle by test_solver_other_optimizers_vs_oracle) run to convergence on FermatPath's convex loss
+    — the derivative of a contracting iteration converges to the implicit derivative.  Smooth logic, so that the
+    validity depends on the interaction points themselves and theta_bar is not zero (with hard logic the envelope
+    theorem removes the implicit term: the power depends on theta* only through the minimised length)."""
+    sc = H.generic_position(SCENES["square"])
+    X, Y = H.jittered_grid(sc, 14, 16, seed=8)
+    X, Y = np.ascontiguousarray(X, np.float32), np.ascontiguousarray(Y, np.float32)
+    grid = np.stack([X, Y], -1).reshape(-1, 2)
+    xys, _, _ = sc.packed_objects()
+    fixed = np.stack([p.xy for p in sc.transmitters.values()])
+    x0 = np.full((5, 1), 0.5, np.float32)
+    Zbar = (0.5 + np.random.default_rng(7).random(X.shape)).astype(np.float32).reshape(-1)
+    kw = dict(min_order=1, max_order=1, method="fermat", mode="hard_sigmoid", grid_cols=X.shape[1], reduce_all=True)
+    new = F.power_bwd(F.TraceConfig(optimizer="newton", steps=30, **kw), xys, fixed, grid, Zbar, x0=x0, alpha=8.0, device="cuda")
+    sgd = F.power_bwd(F.TraceConfig(optimizer="sgd", opt_b1=0.0, lr=0.02, steps=4000, **kw), xys, fixed, grid, Zbar, x0=x0,
+                      alpha=8.0, device="cuda")
+    zn, zs = new["Z"].cpu().numpy(), sgd["Z"].cpu().numpy()
+    same = np.isclose(zn, zs, rtol=1e-4, atol=1e-6 * np.abs(zs).max())
+    assert same.mean() > 0.95, same.mean()
+    gn, gs = new["grid"].cpu().numpy().reshape(-1, 2)[same], sgd["grid"].cpu().numpy().reshape(-1, 2)[same]
+    rel = np.abs(gn - gs).max() / np.abs(gs).max()
+    assert rel < 5e-3, f"receiver cotangents: Newton (implicit) vs converged gradient descent differ by {rel:.2e}"
+    assert np.abs(gs).max() > 0
+    if same.all():
+        for k in ("objects", "fixed", "alpha"):
+            a, b = new[k].cpu().numpy().reshape(-1), sgd[k].cpu().numpy().reshape(-1)
+            assert np.abs(a - b).max() <= 5e-3 * max(np.abs(b).max(), 1e-30), k
+
+
+def test_scene_api_accepts_optimizer_descriptors():
+    from tests.test_gpu_parity import _vertex_scene
+
+    sc = _vertex_scene()
+    X, Y = sc.grid(24, 20)
+    isv = lambda o: isinstance(o, d.Vertex)  # noqa: E731
+    base = dict(path_cls=d.FermatPath, reduce_all=True, max_order=1, key=1234, approx=False, filter_objects=isv)
+    Za = sc.accumulate_on_receivers_grid_over_paths(X, Y, **base)
+    Zb = sc.accumulate_on_receivers_grid_over_paths(X, Y, path_cls_kwargs={"optimizer": d.optimizers.adam(0.1)}, **base)
+    assert np.array_equal(Za, Zb)  # optimize.py:83: adam(0.1) IS the default
+    Zc = sc.accumulate_on_receivers_grid_over_paths(
+        X, Y, path_cls_kwargs={"optimizer": d.optimizers.newton(), "steps": 10}, **base)
+    assert np.isfinite(Zc).all() and (Zc > 0).any()
+    with pytest.raises(NotImplementedError):
+        sc.accumulate_on_receivers_grid_over_paths(X, Y, path_cls_kwargs={"optimizer": object()}, **base)
