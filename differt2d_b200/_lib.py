@@ -89,7 +89,7 @@ class D2DPathRecord(C.Structure):
 
 EXPORTS = [
     "d2d_problem_defaults", "d2d_candidates_count", "d2d_candidates_host", "d2d_candidates_device",
-    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_paths", "d2d_power_host", "d2d_host_release", "d2d_sanitise_scene", "d2d_affine_points", "d2d_launch_count",
+    "d2d_problem_num_candidates", "d2d_active_mask_words", "d2d_power_fwd", "d2d_power_bwd", "d2d_paths", "d2d_power_host", "d2d_host_release", "d2d_sanitise_scene", "d2d_affine_points", "d2d_paths_vjp", "d2d_launch_count",
     "d2d_fma_peak_launch", "d2d_last_error", "d2d_abi_version",
 ]
 
@@ -134,6 +134,9 @@ def lib() -> C.CDLL:
         L.d2d_sanitise_scene.restype = C.c_int
         L.d2d_affine_points.argtypes = [vp, C.c_int64, vp, vp, vp]
         L.d2d_affine_points.restype = C.c_int
+    if hasattr(L, "d2d_paths_vjp") or not os.environ.get("D2D_B200_LIB"):
+        L.d2d_paths_vjp.argtypes = [P, C.c_int64, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+        L.d2d_paths_vjp.restype = C.c_int
     L.d2d_host_release.argtypes = []
     L.d2d_host_release.restype = None
     L.d2d_launch_count.argtypes = []

@@ -31,6 +31,7 @@ UNITS = [("d2d_backward.cu", f"d2d_backward_solver_m{m}.o", ["-fmad=false", f"-D
 UNITS += [("d2d_paths.cu", f"d2d_paths_m{m}.o", ["-fmad=false", f"-DD2D_TU_MODE={m}"]) for m in (1, 0, 2)]
 UNITS += [("d2d_nan.cu", "d2d_nan.o", ["-fmad=false"])]
 UNITS += [("d2d_sanitise.cu", "d2d_sanitise.o", ["-fmad=false"])]
+UNITS += [("d2d_paths_bwd.cu", "d2d_paths_bwd.o", ["-fmad=false"])]
 UNITS += [("d2d_abi.cu", "d2d_abi.o", [])]
 
 

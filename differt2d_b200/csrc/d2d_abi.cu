@@ -355,6 +355,23 @@ int d2d_paths(const D2DProblem* p, float min_valid, int32_t emit_all, D2DPathRec
     return e == 0 ? D2D_OK : cuda_fail(e, "paths_kernel");
 }
 
+int d2d_paths_vjp(const D2DProblem* p, int64_t n_records, const int32_t* rec_fixed, const int64_t* rec_grid,
+                  const int64_t* rec_candidate, const float* valid_bar, const float* xys_bar, float* grid_bar,
+                  float* objects_bar, float* phis_bar, float* fixed_bar, float* alpha_bar, void* stream) {
+    d2d::KParams k;
+    const int rc = pack(p, k);
+    if (rc != D2D_OK) return rc;
+    if (p->method != D2D_METHOD_IMAGE) return fail(D2D_ERR_UNSUPPORTED, "d2d_paths_vjp covers ImagePath only");
+    if (n_records < 0 || (n_records > 0 && (!rec_fixed || !rec_grid || !rec_candidate || !valid_bar || !xys_bar)))
+        return fail(D2D_ERR_INVALID_ARGUMENT, "record arrays / cotangents are NULL");
+    d2d::BwdOut out{nullptr, grid_bar, objects_bar, phis_bar, fixed_bar, alpha_bar};
+    long long nl = 0;
+    const int e = d2d::launch_paths_vjp(k, p->mode, p->grid_role, n_records, rec_fixed, (const long long*)rec_grid,
+                                        (const long long*)rec_candidate, valid_bar, xys_bar, out, (cudaStream_t)stream, &nl);
+    g_launches += nl;
+    return e == 0 ? D2D_OK : cuda_fail(e, "paths_vjp_kernel");
+}
+
 int d2d_sanitise_scene(const float* xys, const uint8_t* kinds, const float* phis, int32_t n, const float* points,
                        int64_t n_points, int32_t drop_zero_length, int32_t normalise, float* xys_out, uint8_t* kinds_out,
                        float* phis_out, int32_t* kept_index, int32_t* n_kept, uint8_t* flags, double* affine, void* stream) {

@@ -125,43 +125,25 @@ __device__ __forceinline__ bool trace_image_tracked(const SceneTab& T, const KPa
     return true;
 }
 
-// Reverse sweep of one traced ImagePath for the upstream cotangent zbar of Z (clean gradients).
-// Fills tx_bar, rx_bar, alpha_bar, oa[] (per interacting object) and the occluder's vertex cotangent (occ_j, occ_bar).
+// Reverse sweep of one traced ImagePath (clean gradients) for the cotangents of its two outputs: the
+// validity (valid_bar) and the path vertices (Xb: in = cotangent of tr.X, used as the accumulator).  Fills tx_bar,
+// rx_bar, alpha_bar, oa[] (per interacting object) and the occluder's vertex cotangent (occ_j, occ_bar).
 template <int MODE, int K>
-__device__ __forceinline__ void image_reverse(const SceneTab& T, const KParams& p, const float alpha, const Cand<K>& cd,
-                                              const ImageTrace<K>& tr, const float zbar, float2& tx_bar, float2& rx_bar,
-                                              float& alpha_bar, ObjAdj (&oa)[K > 0 ? K : 1], int& occ_j, float4& occ_bar) {
+__device__ __forceinline__ void image_reverse_general(const SceneTab& T, const KParams& p, const float alpha,
+                                                      const Cand<K>& cd, const ImageTrace<K>& tr, const float valid_bar,
+                                                      float2 (&Xb)[K + 2], float2& tx_bar, float2& rx_bar,
+                                                      float& alpha_bar, ObjAdj (&oa)[K > 0 ? K : 1], int& occ_j,
+                                                      float4& occ_bar) {
     const float2(&X)[K + 2] = tr.X;
-    float2 Xb[K + 2];
-#pragma unroll
-    for (int i = 0; i < K + 2; ++i) Xb[i] = make_float2(0.f, 0.f);
 #pragma unroll
     for (int i = 0; i < (K > 0 ? K : 1); ++i) oa[i].zero();
     alpha_bar = 0.f;
     occ_j = -1;
-    // (1) fun(path): utils.py:52-54 / length**2 ; path_length geometry.py:199-203
-    {
-        const float val_bar = zbar * tr.valid;
-        float r_bar;
-        if (p.fun == D2D_FUN_RECEIVED_POWER) r_bar = -val_bar * tr.val * 2.0f * fdiv(tr.r, fmaf(tr.r, tr.r, p.h2));
-        else r_bar = val_bar * 2.0f * tr.r;
-#pragma unroll
-        for (int i = 0; i <= K; ++i) {
-            const float dx = (X[i + 1].x - X[i].x) + kEps32;
-            const float dy = (X[i + 1].y - X[i].y) + kEps32;
-            const float sq = fmaf(dx, dx, dy * dy);
-            if (sq > 0.0f) {
-                const float c = r_bar * rsqrtf(sq);
-                Xb[i + 1].x = fmaf(c, dx, Xb[i + 1].x); Xb[i + 1].y = fmaf(c, dy, Xb[i + 1].y);
-                Xb[i].x = fmaf(-c, dx, Xb[i].x); Xb[i].y = fmaf(-c, dy, Xb[i].y);
-            }
-        }
-    }
     // (2) validity (smooth logic only): geometry.py:947-963, logic.py:511-512
     if (MODE != D2D_MODE_HARD) {
         const float v1 = tr.a_on, v2 = 1.0f - tr.a_in, v3 = tr.a_l;
         const int cnt = (v1 == tr.valid) + (v2 == tr.valid) + (v3 == tr.valid);
-        const float share = zbar * tr.val * (cnt == 1 ? 1.0f : (cnt == 2 ? 0.5f : (1.0f / 3.0f)));  // jnp.min: even split
+        const float share = valid_bar * (cnt == 1 ? 1.0f : (cnt == 2 ? 0.5f : (1.0f / 3.0f)));  // jnp.min: even split
         if (v1 == tr.valid && tr.on_i >= 0) {
             // contains_parametric = minimum(act(s - 0), act(1 - s)) (geometry.py:608-621); jnp.minimum's tie rule
             // (1/2, 1/2) applies to the ACTIVATED values, which tie far more often than the pre-activations do
@@ -306,6 +288,34 @@ __device__ __forceinline__ void image_reverse(const SceneTab& T, const KParams& 
     }
     tx_bar = make_float2(Xb[0].x + Ib[0].x, Xb[0].y + Ib[0].y);
     rx_bar = Xb[K + 1];
+}
+
+// The fused `fun` (received_power / length**2, utils.py:52-54; path_length geometry.py:199-203) for the upstream
+// cotangent zbar of Z: d(valid * val) = val dvalid + valid dval.
+template <int MODE, int K>
+__device__ __forceinline__ void image_reverse(const SceneTab& T, const KParams& p, const float alpha, const Cand<K>& cd,
+                                              const ImageTrace<K>& tr, const float zbar, float2& tx_bar, float2& rx_bar,
+                                              float& alpha_bar, ObjAdj (&oa)[K > 0 ? K : 1], int& occ_j, float4& occ_bar) {
+    const float2(&X)[K + 2] = tr.X;
+    float2 Xb[K + 2];
+#pragma unroll
+    for (int i = 0; i < K + 2; ++i) Xb[i] = make_float2(0.f, 0.f);
+    const float val_bar = zbar * tr.valid;
+    float r_bar;
+    if (p.fun == D2D_FUN_RECEIVED_POWER) r_bar = -val_bar * tr.val * 2.0f * fdiv(tr.r, fmaf(tr.r, tr.r, p.h2));
+    else r_bar = val_bar * 2.0f * tr.r;
+#pragma unroll
+    for (int i = 0; i <= K; ++i) {
+        const float dx = (X[i + 1].x - X[i].x) + kEps32;
+        const float dy = (X[i + 1].y - X[i].y) + kEps32;
+        const float sq = fmaf(dx, dx, dy * dy);
+        if (sq > 0.0f) {
+            const float c = r_bar * rsqrtf(sq);
+            Xb[i + 1].x = fmaf(c, dx, Xb[i + 1].x); Xb[i + 1].y = fmaf(c, dy, Xb[i + 1].y);
+            Xb[i].x = fmaf(-c, dx, Xb[i].x); Xb[i].y = fmaf(-c, dy, Xb[i].y);
+        }
+    }
+    image_reverse_general<MODE, K>(T, p, alpha, cd, tr, zbar * tr.val, Xb, tx_bar, rx_bar, alpha_bar, oa, occ_j, occ_bar);
 }
 
 }  // namespace d2d

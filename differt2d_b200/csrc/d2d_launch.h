@@ -38,6 +38,11 @@ int launch_power_fwd(const KParams& p, int mode, int grid_role, int method, floa
 int launch_power_bwd(const KParams& p, int mode, int grid_role, int method, const float* Zbar, const BwdOut& out,
                      cudaStream_t stream, long long* launches);
 
+// reverse mode of the path materialisation (d2d_paths_bwd.cu): cotangents of (valid, xys) per record -> inputs
+int launch_paths_vjp(const KParams& p, int mode, int grid_role, long long n, const int32_t* rec_fixed,
+                     const long long* rec_grid, const long long* rec_candidate, const float* valid_bar,
+                     const float* xys_bar, const BwdOut& out, cudaStream_t stream, long long* launches);
+
 // scene sanitiser (d2d_sanitise.cu)
 int launch_sanitise(const float* xys, const uint8_t* kinds, const float* phis, int n, const float* points,
                     long long n_points, int drop, int normalise, float* xys_out, uint8_t* kinds_out, float* phis_out,

@@ -320,6 +320,44 @@ def paths(cfg: TraceConfig, xys, fixed, grid, *, kinds=None, phis=None, alpha=DE
     return out
 
 
+def paths_vjp(cfg: TraceConfig, xys, fixed, grid, rec: dict, valid_bar: torch.Tensor, xys_bar: torch.Tensor, *, kinds=None,
+              phis=None, alpha=DEFAULT_ALPHA, want=("grid", "objects", "phis", "fixed", "alpha"), device=None) -> dict:
+    """
+    Reverse mode of `paths` (d2d_paths_vjp; ImagePath): pulls the cotangents of the records' validity (valid_bar [n])
+    and vertices (xys_bar [n, MAX_ORDER + 2, 2]) back to the grid points (per fixed point: [T, R, 2]), the fixed points,
+    the object vertices, the RIS angles and alpha.  `rec` is the dict `paths` returned for the SAME problem.
+    """
+    device = torch.device(device) if device is not None else (
+        grid.device if isinstance(grid, torch.Tensor) else torch.device("cuda", torch.cuda.current_device()))
+    pk = _Packed(cfg, xys, kinds, phis, fixed, grid, alpha, None, device)
+    n = int(rec["fixed"].numel())
+    with torch.cuda.device(device):
+        rf = rec["fixed"].to(device=device, dtype=torch.int32).contiguous()
+        rg = rec["grid"].to(device=device, dtype=torch.int64).contiguous()
+        rc_ = rec["candidate"].to(device=device, dtype=torch.int64).contiguous()
+        vb = valid_bar.detach().to(device=device, dtype=torch.float32).reshape(n).contiguous()
+        xb = torch.zeros((max(n, 1), L.MAX_ORDER + 2, 2), dtype=torch.float32, device=device)
+        if n:
+            xb[:n, : xys_bar.shape[1]] = xys_bar.detach().to(device=device, dtype=torch.float32)
+        out = {}
+        if "grid" in want:
+            out["grid"] = torch.empty((pk.T, pk.R, 2), dtype=torch.float32, device=device)
+        if "objects" in want:
+            out["objects"] = torch.empty((pk.N, 2, 2), dtype=torch.float32, device=device)
+        if "phis" in want:
+            out["phis"] = torch.empty((pk.N,), dtype=torch.float32, device=device)
+        if "fixed" in want:
+            out["fixed"] = torch.empty((pk.T, 2), dtype=torch.float32, device=device)
+        if "alpha" in want:
+            out["alpha"] = torch.empty((1,), dtype=torch.float32, device=device)
+        ptr = lambda k: out[k].data_ptr() if k in out else None  # noqa: E731
+        rc = L.lib().d2d_paths_vjp(C.byref(pk.p), n, rf.data_ptr() if n else None, rg.data_ptr() if n else None,
+                                   rc_.data_ptr() if n else None, vb.data_ptr() if n else None, xb.data_ptr() if n else None,
+                                   ptr("grid"), ptr("objects"), ptr("phis"), ptr("fixed"), ptr("alpha"), _stream(device))
+        L.check(rc, "d2d_paths_vjp")
+    return out
+
+
 def power_value_and_vjp(cfg: TraceConfig, xys, fixed, grid, Zbar=None, *, kinds=None, phis=None, alpha=DEFAULT_ALPHA,
                         x0=None, want=("grid", "objects", "phis", "fixed", "alpha"), device=None) -> dict:
     """Z and the requested cotangents (what jax.value_and_grad / jax.vjp deliver): the forward kernel, then the

@@ -352,14 +352,24 @@ class Scene:
         return cfg, alpha, fname == "generic"
 
     def _generic_accumulate(self, cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed, grid, alpha, x0, device,
-                            point_cls=Point):
+                            point_cls=Point, want_grad=False):
         """SURVEY §8 f1 — arbitrary `fun`: Z[t, r] = sum_c valid * fun(transmitter, receiver, path,
         interacting_objects, *fun_args, **fun_kwargs) (scene.py:1909-1916) with the paths materialised by `d2d_paths`
         (every path whose validity is non-zero) and `fun` evaluated ONCE PER ORDER on batched arguments (PointBatch,
         PathBatch, list of ObjectBatch: torch tensors on the device).  `point_cls` is the reference's receiver_cls /
         transmitter_cls: a custom class is constructed as point_cls(xy=<[n, 2] tensor>) for the grid end of the link.
-        The summation runs in index order per (t, r) up to the reduction order of index_add_."""
+        The summation runs in index order per (t, r) up to the reduction order of index_add_.
+
+        want_grad (ImagePath): also d Z[t, r] / d grid[r] — what jax.grad(facc, argnums=1) gives for ANY fun
+        (scene.py:1920-1925).  `fun` is differentiated by torch autograd on the materialised vertices (and on the end
+        points it is handed), which yields the cotangents of every record's validity and vertices; `d2d_paths_vjp`
+        pulls them back through the path construction and the validity logic.  Returns (Z, dZ [T, R, 2])."""
         rec = F.paths(cfg, xys, fixed, grid, kinds=kinds, phis=phis, alpha=alpha, x0=x0, min_valid=0.0, device=device)
+        if want_grad:
+            if cfg.method != "image":
+                raise NotImplementedError("gradients of a generic `fun` are available for ImagePath only")
+            rec["xys"] = rec["xys"].detach().clone().requires_grad_(True)
+            rec["valid"] = rec["valid"].detach().clone().requires_grad_(True)
         fixed_t = torch.as_tensor(np.asarray(fixed, dtype=np.float32).reshape(-1, 2), device=device)
         T, R = fixed_t.shape[0], grid.shape[0]
         xys_t = torch.as_tensor(np.asarray(xys, dtype=np.float32).reshape(-1, 2, 2), device=device)
@@ -378,8 +388,12 @@ class Scene:
                 continue
             fi, gi = rec["fixed"][sel].to(torch.int64), rec["grid"][sel]
             batch = PathBatch(rec["xys"][sel][:, : k + 2], rec["valid"][sel], rec["loss"][sel], k)
-            fixed_pts = PointBatch(fixed_t[fi])
-            grid_pts = PointBatch(grid[gi]) if point_cls is Point else point_cls(xy=grid[gi])
+            # the end points a `fun` sees ARE the first / last path vertices (same values; under want_grad the same
+            # autograd leaves, so that a `fun` written on transmitter.xy / receiver.xy is differentiated too)
+            first, last = batch.xys[:, 0], batch.xys[:, k + 1]
+            fixed_xy, grid_xy = (first, last) if cfg.grid_role == "receivers" else (last, first)
+            fixed_pts = PointBatch(fixed_xy)
+            grid_pts = PointBatch(grid_xy) if point_cls is Point else point_cls(xy=grid_xy)
             tx, rx = (fixed_pts, grid_pts) if cfg.grid_role == "receivers" else (grid_pts, fixed_pts)
             objs = []
             if k > 0:
@@ -388,7 +402,20 @@ class Scene:
             val = torch.as_tensor(fun(tx, rx, batch, objs, *fun_args, **dict(fun_kwargs or {})), dtype=torch.float32,
                                   device=device)
             val = val.expand(batch.valid.shape)
-            Z.index_add_(0, fi * R + gi, batch.valid * val)
+            Z = Z.index_add(0, fi * R + gi, batch.valid * val)
+        if want_grad:
+            # every record belongs to ONE (fixed point, grid point): the cotangent ones of sum(Z) reaches each of them
+            if Z.requires_grad:
+                vbar, xbar = torch.autograd.grad(Z.sum(), [rec["valid"], rec["xys"]], allow_unused=True)
+            else:
+                vbar = xbar = None
+            vbar = torch.zeros_like(rec["valid"]) if vbar is None else vbar
+            xbar = torch.zeros_like(rec["xys"]) if xbar is None else xbar
+            # (the vertices handed to `fun` as path.xys include the two end points: rows 0 and order + 1)
+            g = F.paths_vjp(cfg, xys, fixed, grid, rec, vbar, xbar, kinds=kinds, phis=phis, alpha=alpha, want=("grid",),
+                            device=device)["grid"]
+            Z = Z.detach().reshape(T, R)
+            return (Z.sum(0), g.sum(0)) if cfg.reduce_all else (Z, g)
         Z = Z.reshape(T, R)
         return Z.sum(0) if cfg.reduce_all else Z
 
@@ -456,7 +483,14 @@ class Scene:
         back = (lambda t: t.cpu().numpy()) if as_numpy else (lambda t: t.to(Xt.device))
         want_grad = grad or value_and_grad
         if generic and want_grad:
-            raise NotImplementedError("gradients of a generic `fun` are not fused; use received_power / length_squared")
+            Z, dZ = self._generic_accumulate(cfg, fun, fun_args, fun_kwargs, xys, kinds, phis, fixed, grid, alpha, x0,
+                                             device, point_cls, want_grad=True)
+            if reduce_all:
+                Z, dZ = back(Z.reshape(shape)), back(dZ.reshape(*shape, 2))
+                return (Z, dZ) if value_and_grad else dZ
+            if value_and_grad:
+                return ((k, (back(Z[i].reshape(shape)), back(dZ[i].reshape(*shape, 2)))) for i, k in enumerate(names))
+            return ((k, back(dZ[i].reshape(*shape, 2))) for i, k in enumerate(names))
         tracked = None if generic else self._tracked_tensors(grid_role, device)
         diff = tracked is not None or (isinstance(alpha, torch.Tensor) and alpha.requires_grad) or \
             (isinstance(X, torch.Tensor) and (X.requires_grad or Y.requires_grad))

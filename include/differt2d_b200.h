@@ -205,6 +205,19 @@ int d2d_paths(const D2DProblem *p, float min_valid, int32_t emit_all, D2DPathRec
               unsigned long long *count, void *stream);
 
 /*
+ * Reverse mode of d2d_paths — gradients of a GENERIC `fun` (scene.py:1892-1925 differentiates acc = sum valid * fun(...)
+ * for any python callable).  The host framework evaluates and differentiates `fun` on the materialised vertices, which
+ * gives, per emitted record, valid_bar = d acc / d valid and xys_bar = d acc / d xys ([n, D2D_MAX_ORDER + 2, 2], rows
+ * beyond order + 2 ignored); this call pulls them back through path construction and validity logic (ImagePath only:
+ * D2D_ERR_UNSUPPORTED otherwise).  rec_fixed / rec_grid / rec_candidate: the `fixed`, `grid`, `candidate` fields of the
+ * records (device arrays, any order).  Outputs as d2d_power_bwd, OVERWRITTEN, each optional; grid_bar is always
+ * [n_fixed, R, 2] (per fixed point).  Records whose validity is exactly 0 contribute nothing (clean gradients).
+ */
+int d2d_paths_vjp(const D2DProblem *p, int64_t n_records, const int32_t *rec_fixed, const int64_t *rec_grid,
+                  const int64_t *rec_candidate, const float *valid_bar, const float *xys_bar, float *grid_bar,
+                  float *objects_bar, float *phis_bar, float *fixed_bar, float *alpha_bar, void *stream);
+
+/*
  * Scene sanitiser on the device.  Scene.from_geojson (scene.py:628-663) emits one ZERO-LENGTH closure wall
  * per closed polygon ring (coords[i-1] wraps to the duplicated vertex): every candidate through it is invalid, and the
  * reference's own reverse mode turns NaN for the whole map (geometry.py:1105); raw lon/lat coordinates add ~3 % of a wall

@@ -857,8 +857,9 @@ def test_generic_fun_escape_hatch():
         X, Y, fun=lambda tx, rx, p, objs, s: s * p.length() ** 2, fun_args=(2.0,), max_order=0, approx=False))
     assert [k for k, _ in res] == ["tx"]
     np.testing.assert_allclose(res[0][1], 2.0 * ((X - 0.2) ** 2 + (Y - 0.2) ** 2), rtol=1e-5, atol=1e-6)
-    with pytest.raises(NotImplementedError):
-        sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=my_power, grad=True)
+    with pytest.raises(NotImplementedError):  # gradients of a generic fun: ImagePath only
+        d.Scene.square_scene().accumulate_on_receivers_grid_over_paths(X, Y, fun=my_power, grad=True, path_cls=d.FermatPath,
+                                                                     key=1)
 
 
 def test_all_valid_paths_fermat_on_vertex_scene():

@@ -727,3 +727,51 @@ def test_scene_api_accepts_optimizer_descriptors():
     assert np.isfinite(Zc).all() and (Zc > 0).any()
     with pytest.raises(NotImplementedError):
         sc.accumulate_on_receivers_grid_over_paths(X, Y, path_cls_kwargs={"optimizer": object()}, **base)
+
+
+# ---- gradients of a generic `fun` -------------------------------------------------------------------------
+@pytest.mark.parametrize("approx", [False, True])
+@pytest.mark.parametrize("role", ["receivers", "transmitters"])
+def test_generic_fun_gradients_match_the_fused_kernels(approx, role):
+    """scene.py:1920-1925 differentiates acc = sum valid * fun(tx, rx, path, objects) for ANY fun.  A python restatement of
+    utils.received_power, evaluated and differentiated by torch autograd on the materialised vertices and pulled back by
+    d2d_paths_vjp, must give the fused backward kernel's grad / value_and_grad (per fixed point and reduced)."""
+    sc = H.generic_position(SCENES["obstacle"]).update_receivers(rx2=d.Point(xy=[0.8, 0.3]))
+    X, Y = H.jittered_grid(sc, 14, 16, seed=4)
+
+    def my_power(transmitter, receiver, path, interacting_objects, r_coef=0.5, height=0.1):
+        r = path.length()
+        return (r_coef ** len(interacting_objects)) / (height * height + r * r)
+
+    call = sc.accumulate_on_receivers_grid_over_paths if role == "receivers" else sc.accumulate_on_transmitters_grid_over_paths
+    kw = dict(max_order=2, approx=approx, alpha=30.0)
+    Zg, dZg = call(X, Y, fun=my_power, reduce_all=True, value_and_grad=True, **kw)
+    Zf, dZf = call(X, Y, reduce_all=True, value_and_grad=True, **kw)
+    np.testing.assert_allclose(Zg, Zf, rtol=2e-6, atol=1e-7)
+    scale = np.abs(dZf).max()
+    np.testing.assert_allclose(dZg, dZf, rtol=1e-4, atol=1e-5 * scale)
+    assert scale > 0
+    per_g = dict(call(X, Y, fun=my_power, grad=True, **kw))
+    per_f = dict(call(X, Y, grad=True, **kw))
+    assert list(per_g) == list(per_f)
+    for k in per_f:
+        assert per_g[k].shape == (*X.shape, 2)
+        np.testing.assert_allclose(per_g[k], per_f[k], rtol=1e-4, atol=1e-5 * np.abs(per_f[k]).max())
+
+
+def test_generic_fun_gradient_through_the_end_points():
+    """A fun written on the END POINTS it is handed (transmitter.xy, receiver.xy), reference LOS KAT style
+    (tests/test_scene.py:487-627: maps X^2 + Y^2, gradients [2X, 2Y])."""
+    sc = d.Scene(transmitters={"tx": d.Point(xy=[0.25, -0.5])}, receivers={"rx": d.Point(xy=[0.0, 0.0])}, objects=[])
+    x = np.linspace(-2, 2, 12, dtype=np.float32)
+    y = np.linspace(-1, 3, 9, dtype=np.float32)
+    X, Y = np.meshgrid(x, y)
+
+    def dist2(transmitter, receiver, path, interacting_objects):
+        dlt = receiver.xy - transmitter.xy
+        return (dlt * dlt).sum(-1)
+
+    Z, dZ = sc.accumulate_on_receivers_grid_over_paths(X, Y, fun=dist2, reduce_all=True, value_and_grad=True,
+                                                       max_order=0, approx=False)
+    np.testing.assert_allclose(Z, (X - 0.25) ** 2 + (Y + 0.5) ** 2, rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(dZ, np.stack([2 * (X - 0.25), 2 * (Y + 0.5)], -1), rtol=1e-5, atol=1e-5)
