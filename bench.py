@@ -161,12 +161,16 @@ class ClockSampler:
         sm, bits, power, sm_max = [], 0, [], None
         for ln in text.splitlines():
             f = ln.split()
-            if f and f[0] == "max":
-                sm_max = float(f[1])
-            elif f and f[0] == "s" and self.t0 is not None and self.t0 <= float(f[1]) <= self.t1:
-                sm.append(float(f[2]))
-                bits |= int(f[3])
-                power.append(float(f[4]))
+            try:  # (the last line may be cut short: the sampler is terminated while it writes)
+                if len(f) == 2 and f[0] == "max":
+                    sm_max = float(f[1])
+                elif len(f) == 5 and f[0] == "s" and self.t0 is not None and self.t0 <= float(f[1]) <= self.t1:
+                    c, b, w = float(f[2]), int(f[3]), float(f[4])
+                    sm.append(c)
+                    bits |= b
+                    power.append(w)
+            except ValueError:
+                continue
         if not sm:
             return self._smi_once("no NVML sample fell inside the timed region")
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": sm_max,
@@ -542,20 +546,22 @@ def parity_spotcheck(job, Z, gbar) -> dict:
     # well conditioned in fp32: the oracle's own fp32 evaluation is within 1e-5 of its fp64 value (an order below the
     # bar, so that a second fp32 evaluation of the same size of error — the kernel's — can be held to rtol 1e-4)
     agree = np.abs(w32 - w64) <= 1e-5 * np.abs(w64) + 1e-7 * scale
-    err = np.abs(gg - w32) / (np.abs(w32) + 1e-6 * scale)
+    tol = 1e-4 * np.abs(w32) + 1e-6 * scale  # the elementwise bar of the tests (tests/test_gpu_parity._close)
+    err = np.abs(gg - w32) / tol
     noise = np.abs(w32 - w64)
-    within_noise = np.abs(gg - w32) <= 1e-4 * np.abs(w32) + 1e-6 * scale + 4.0 * noise + 4.0 * np.percentile(noise, 90)
+    within_noise = np.abs(gg - w32) <= tol + 4.0 * noise + 4.0 * np.percentile(noise, 90)
     g_rel = float(err[agree].max()) if agree.any() else None
     return {"points": int(got.size), "max_rel": z_rel, "nonzero_points": int((Zo != 0).sum()),
             "z": "Z of the timed loop's last forward launch vs oracle/d2d_oracle.c on a strided 64x64 subset",
             "grid_bar": {"entries": int(w32.size), "nonzero": int((w32 != 0).sum()),
-                         "well_conditioned_entries": int(agree.sum()), "max_rel_on_those": g_rel,
+                         "well_conditioned_entries": int(agree.sum()), "max_err_over_tol_on_those": g_rel,
+                         "tol": "|kernel - oracle32| <= 1e-4 |oracle32| + 1e-6 max|oracle32| (elementwise)",
                          "all_within_oracle_fp32_noise": bool(within_noise.all()),
                          "vs": "dual-number VJP of oracle/d2d_oracle_ad.cpp in fp32; 'well conditioned' = its fp32 and fp64 "
                                "evaluations agree to 1e-5 (raw lon/lat coordinates put fp32 noise on the reference's own "
                                "cotangents, tests/test_gpu_parity_round2.py); everywhere: |kernel - oracle32| <= rtol 1e-4 "
                                "+ 4 |oracle32 - oracle64| + 4 P90"},
-            "ok": bool(z_rel <= 1e-5 and (g_rel is None or g_rel <= 1e-4) and within_noise.all())}
+            "ok": bool(z_rel <= 1e-5 and (g_rel is None or g_rel <= 1.0) and within_noise.all())}
 
 
 def main() -> None:
@@ -673,7 +679,12 @@ def main() -> None:
     # kernels of this library inside the timed region: 2 per step (forward, backward); a graph replay launches the
     # captured kernels without passing through the library's counter
     launches = 2 * args.steps if graphed else F.launch_count() - launches0
-    clocks = sampler.stop() if rank == 0 else None
+    clocks = None
+    if rank == 0:
+        try:
+            clocks = sampler.stop()
+        except Exception as e:  # noqa: BLE001  (the sampler must never take the measurement down)
+            clocks = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [f"clock sampler failed: {e!r}"[:200]], "samples": 0}
     elapsed_ms = t_start.elapsed_time(t_end)
     if dist is not None:
         elapsed_ms = D.max_over_ranks(elapsed_ms, dev)
@@ -731,7 +742,7 @@ def main() -> None:
     graphs = [job.graph]
     if not args.no_extras:
         # strong-scaling leg (BASELINE config 3: 2048 x 2048 in total), every rank takes part
-        if args.scaling == "weak":
+        if args.scaling == "weak":  # (every rank takes part: collectives inside; errors here are fatal on purpose)
             sjob = CityJob(torch, L, F, D, sc, GRID_STRONG[0], GRID_STRONG[1], world, rank, dev)
             for _ in range(2):
                 sjob.step_eager(flush)
@@ -746,7 +757,10 @@ def main() -> None:
                 "note": "BASELINE config 3 (2048x2048 receivers in total, row-sharded); same step as the headline"}
             del sjob
         if rank == 0:
-            extras["dense"] = dense_leg(torch, L, F, dev, flush, min(args.steps, 10), peak_tf)
+            try:
+                extras["dense"] = dense_leg(torch, L, F, dev, flush, min(args.steps, 10), peak_tf)
+            except Exception as e:  # noqa: BLE001
+                extras["dense_error"] = repr(e)[:300]
             try:
                 extras["parity_spotcheck"] = parity_spotcheck(job, job.Z, job.gbar)
             except Exception as e:  # noqa: BLE001
@@ -837,7 +851,7 @@ def main() -> None:
     }
     if not graphed and not args.no_graph:
         line["cuda_graph_error"] = getattr(job, "graph_error", None)
-    for k in ("strong", "parity_spotcheck"):
+    for k in ("strong", "parity_spotcheck", "dense_error"):
         if k in extras:
             line[k] = extras[k]
     if world == 1 and not args.no_cpu_baseline:

@@ -115,6 +115,18 @@ def main():
             ms = timed(lambda: F.power_fwd(cfg, xys, fixed, grid, kinds=kinds, phis=phis, x0=x0, device="cuda"), a.steps)
             emit(f"cfg4: basic scene + vertex, {method} orders 0-2, 100 Adam steps, 1024x1024, hard, forward", ms,
                  1024 * 1024 * C, adam_steps_per_s=1024 * 1024 * (C - 1) * 100 / (ms * 1e-3))
+            cfgn = F.TraceConfig(mode="hard", max_order=2, method=method, steps=30, optimizer="newton", grid_cols=1024)
+            ms = timed(lambda: F.power_fwd(cfgn, xys, fixed, grid, kinds=kinds, phis=phis, x0=x0, device="cuda"), a.steps)
+            emit(f"cfg4: same, {method}, 30 damped Newton iterations (non-parity fast mode), forward", ms, 1024 * 1024 * C)
+            cfgs = F.TraceConfig(mode="hard_sigmoid", max_order=2, method=method, steps=30, optimizer="newton", grid_cols=1024,
+                                 reduce_all=True)
+            ms = timed(lambda: F.power_value_and_vjp(cfgs, xys, fixed, grid, None, kinds=kinds, phis=phis, x0=x0, alpha=100.0,
+                                                     device="cuda"), a.steps)
+            emit(f"cfg4: same, {method}, Newton, hard_sigmoid, forward + implicit VJP", ms, 1024 * 1024 * C)
+            cfga = F.TraceConfig(mode="hard_sigmoid", max_order=2, method=method, steps=100, grid_cols=1024, reduce_all=True)
+            ms = timed(lambda: F.power_value_and_vjp(cfga, xys, fixed, grid, None, kinds=kinds, phis=phis, x0=x0, alpha=100.0,
+                                                     device="cuda"), a.steps)
+            emit(f"cfg4: same, {method}, 100 Adam steps, hard_sigmoid, forward + VJP through the scan", ms, 1024 * 1024 * C)
     if want("cfg5a"):
         sc = d.Scene.square_scene().add_objects(d.RIS(xys=[[0.5, 0.3], [0.5, 0.7]], phi=float(np.pi / 4)))
         xys, kinds, phis, fixed, grid = pack(sc, 300)
