@@ -788,17 +788,18 @@ def main() -> None:
         ncu = json.load(open(os.path.join(ROOT, "profiles", "ncu_metrics.json")))
     except Exception:  # noqa: BLE001
         pass
-    nk = ncu.get("kernels", {})
+    nk, nd = ncu.get("kernels", {}), ncu.get("dense", {})
     traffic = None
     capture = None
-    if dom in nk:
-        traffic = nk[dom]["dram_bytes_read"] + nk[dom]["dram_bytes_write"]
-        capture = {k: nk[dom][k] for k in ("issue_slots_busy_pct", "fp32_lanes_busy_pct", "executed_fp32_flop",
-                                           "warp_instructions", "achieved_occupancy_pct") if k in nk[dom]}
-        ex_tf = nk[dom]["executed_fp32_flop"] / (nk[dom]["duration_ms_under_ncu"] * 1e-3) / 1e12
-        capture["fp32_tflops"] = ex_tf
-        capture["source"] = ("profiles/ncu_metrics.json: a COMMITTED `ncu --set full` capture of this command "
-                             f"({ncu.get('capture', 'see profiles/README.md')}); constants, not measured by this run")
+    keys = ("duration_ms_under_ncu", "issue_slots_busy_pct", "fp32_lanes_busy_pct", "executed_fp32_flop", "warp_instructions",
+            "achieved_occupancy_pct", "registers_per_thread", "stall_no_instruction_per_issue", "dram_bytes_read", "dram_bytes_write")
+    if nd:  # DRAM bytes of one step of the un-prunable leg (the leg roofline.frac is measured on), per launch pair
+        traffic = sum(v["dram_bytes_read"] + v["dram_bytes_write"] for v in nd.values())
+    if nk or nd:
+        capture = {"headline_step": {k: {a: v[a] for a in keys if a in v} for k, v in nk.items()},
+                   "dense_leg": {k: {a: v[a] for a in keys if a in v} for k, v in nd.items()},
+                   "source": ("profiles/ncu_metrics.json: a COMMITTED `ncu --set full` capture of this command "
+                              f"({ncu.get('capture', 'see profiles/README.md')}); constants, NOT measured by this run")}
     dense = extras.get("dense")
     algo_bytes = R * (8 + 4 + 4 + 8)
     hbm_peak = 6650.0

@@ -48,8 +48,14 @@ constexpr int kBlock = 128;
 #ifndef D2D_BWD_MIN_CTAS
 #if defined(D2D_TU_SOLVER) && D2D_TU_SOLVER
 #define D2D_BWD_MIN_CTAS 5  // FermatPath / MinPath: the reverse sweep through the scan keeps far more state alive
+#elif defined(D2D_TU_MODE) && D2D_TU_MODE == D2D_MODE_SIGMOID
+// sigmoid never saturates: (nearly) every path runs the reverse sweep, whose live state does not fit 64 registers —
+// at 8 CTAs/SM the un-prunable leg spilt 0.5 GB per launch to DRAM (ncu, r02n) for a 1 % gain: 96 registers there
+#define D2D_BWD_MIN_CTAS 5
 #else
-#define D2D_BWD_MIN_CTAS 8  // ImagePath: 64 registers; measured 8 > 6 > 5 > 4 > 3 CTAs/SM on both bench legs (r02g, r02j)
+// hard / hard_sigmoid: the sweep runs for the few paths with a non-zero validity, the re-trace wants occupancy:
+// 64 registers; measured 8 > 6 > 5 > 4 > 3 CTAs/SM (r02g, r02j)
+#define D2D_BWD_MIN_CTAS 8
 #endif
 #endif
 constexpr int kTileCols = 16;
