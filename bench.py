@@ -459,11 +459,14 @@ class CityJob:
 
 def dense_leg(torch, L, F, dev, flush, steps, peak_tf):
     """
-    The un-prunable regime (BASELINE config 2, examples/plot_power_profiles.py:118 alpha sweep): obstacle scene (8 walls),
+    The dense regime (BASELINE config 2, examples/plot_power_profiles.py:118 alpha sweep): obstacle scene (8 walls),
     orders 0-2 (65 candidates), sigmoid, alpha = 1, 1024 x 1024 receivers, forward + VJP.  sigmoid(alpha x) is never
-    exactly 0 or 1 at alpha = 1, so no cull, early exit or activity mask removes anything: every (receiver, candidate)
-    path is traced by the forward launch and re-traced and reversed by the backward launch.  Algorithmic flop of
-    SURVEY §8(d) (VJP = 2 x forward) / measured time / measured FP32 FMA peak.
+    exactly 0 or 1 at alpha = 1, so no cull, early exit or activity mask removes a path: every (receiver, candidate)
+    path is constructed, tested, valued and accumulated by the forward launch, and re-traced and reversed by the
+    backward launch.  The one thing the kernels still avoid (exactly) is the occlusion fold of a path whose validity
+    cannot depend on it (fold_skip_bound, csrc/d2d_device.cuh: min(a_on, a_l) <= 1 - act(0.51)): ~3/4 of the paths.
+    Algorithmic flop of SURVEY §8(d) (VJP = 2 x forward; the skipped folds still count, as everywhere else) /
+    measured time / measured FP32 FMA peak.
     """
     import differt2d_b200 as d
 
@@ -508,7 +511,8 @@ def dense_leg(torch, L, F, dev, flush, steps, peak_tf):
     alive = float((Z != 0).float().mean())
     out = {
         "workload": "BASELINE config 2: square_scene_with_obstacle, ImagePath orders 0-2 (65 candidates), sigmoid "
-                    "alpha=1, 1024x1024 receivers, forward + VJP (receivers, vertices, TX, alpha); nothing is prunable",
+                    "alpha=1, 1024x1024 receivers, forward + VJP (receivers, vertices, TX, alpha); every path is traced, valued "
+                    "and reversed (validity never 0); the occlusion fold is skipped where it provably cannot change the validity",
         "steps": steps, "fwd_ms": fwd, "bwd_ms": bwd, "ms": fwd + bwd,
         "algorithmic_flop": {"fwd": f_fwd, "vjp": 2.0 * f_fwd, "total": 3.0 * f_fwd},
         "achieved_tflops": 3.0 * f_fwd / ((fwd + bwd) * 1e-3) / 1e12,
@@ -576,7 +580,7 @@ def main() -> None:
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue the step eagerly instead of replaying a CUDA graph")
     ap.add_argument("--no-extras", action="store_true", help="skip the dense leg, the strong-scaling leg and the spot check")
-    ap.add_argument("--only-dense", action="store_true", help="profiling aid: run the un-prunable leg alone and print it")
+    ap.add_argument("--only-dense", action="store_true", help="profiling aid: run the dense leg alone and print it")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -793,7 +797,7 @@ def main() -> None:
     capture = None
     keys = ("duration_ms_under_ncu", "issue_slots_busy_pct", "fp32_lanes_busy_pct", "executed_fp32_flop", "warp_instructions",
             "achieved_occupancy_pct", "registers_per_thread", "stall_no_instruction_per_issue", "dram_bytes_read", "dram_bytes_write")
-    if nd:  # DRAM bytes of one step of the un-prunable leg (the leg roofline.frac is measured on), per launch pair
+    if nd:  # DRAM bytes of one step of the dense leg (the leg roofline.frac is measured on), per launch pair
         traffic = sum(v["dram_bytes_read"] + v["dram_bytes_write"] for v in nd.values())
     if nk or nd:
         capture = {"headline_step": {k: {a: v[a] for a in keys if a in v} for k, v in nk.items()},
@@ -809,7 +813,7 @@ def main() -> None:
         pass
     roofline = {
         "bound": "fp32",
-        "kernel": "power_fwd_kernel + power_bwd_kernel on the un-prunable leg (BASELINE config 2, sigmoid alpha=1)",
+        "kernel": "power_fwd_kernel + power_bwd_kernel on the dense leg (BASELINE config 2, sigmoid alpha=1)",
         "achieved": dense["achieved_tflops"] if dense else None, "peak": peak_tf, "unit": "TFLOP/s",
         "frac": dense["frac_of_fp32_fma_peak"] if dense else None,
         "traffic": traffic,
@@ -820,7 +824,11 @@ def main() -> None:
                    "FMUL + FADD (1 flop per slot) and every IEEE division / sqrt costs 8-10 slots for the 1 flop the "
                    "convention credits: the attainable fraction for this arithmetic contract is below 0.5",
         "frac_definition": "ALGORITHMIC flop of SURVEY §8(d) (forward + VJP = 3 x F_fwd) of the dense leg / its measured "
-                           "time / peak: nothing is pruned there, so algorithmic work is executed work",
+                           "time / peak.  No path is pruned there (every path is constructed, tested, valued, accumulated and "
+                           "reversed); the occlusion fold — about half of F_fwd — is skipped, exactly, for the ~3/4 of the "
+                           "paths whose validity cannot depend on it, and still counted (SURVEY §8(d): no early-out "
+                           "credit).  What the SMs executed is under ncu_capture.dense_leg (executed_fp32_flop, "
+                           "fp32_lanes_busy_pct, issue_slots_busy_pct)",
         "dense_leg": dense,
         "algorithmic": {
             "note": "SURVEY §8(d) convention on the HEADLINE workload (pruned work still counted; VJP = 2 x forward): exact "

@@ -69,6 +69,54 @@ __device__ __forceinline__ void residual_adj(const int kind, const float2 a, con
     b_bar.x -= rv_bar.x; b_bar.y -= rv_bar.y;
 }
 
+// VJP of normalize (v_hat = v / len) from the unit vector and the length the forward produced: no square root, one fast
+// reciprocal (the sweep feeds no predicate).  len == 1 with v_hat == v for a zero-length segment (v / 1): the
+// projection term then vanishes with |v|^2 and the cotangent passes through, like the `where` of geometry.py:227-230.
+__device__ __forceinline__ float2 normalize_adj_hat(const float2 vh, const float len, const float2 vh_bar) {
+    const float inv = __fdividef(1.0f, len);
+    const float pr = dot2(vh_bar, vh);
+    return make_float2((vh_bar.x - pr * vh.x) * inv, (vh_bar.y - pr * vh.y) * inv);
+}
+
+// residual_adj() from the unit directions i = normalize(b - a), r = normalize(c - b) and lengths the trace kept
+// (path_loss_dirs): the residual vector e is formed from the forward's own bits, as in residual_adj.
+__device__ __forceinline__ void residual_adj_dirs(const int kind, const float2 i, const float li, const float2 r,
+                                                  const float lr, const float4 w1, const float2 sc, const float g,
+                                                  float2& a_bar, float2& b_bar, float2& c_bar, float2& n_bar,
+                                                  float& phi_bar) {
+    if (kind == D2D_KIND_VERTEX) return;
+    const float2 n = make_float2(w1.x, w1.y);
+    float2 r_bar;
+    if (kind == D2D_KIND_WALL) {
+        const float c2 = 2.0f * dot2(i, n);
+        const float2 e = make_float2(r.x - (i.x - c2 * n.x), r.y - (i.y - c2 * n.y));
+        const float2 e_bar = make_float2(2.0f * g * e.x, 2.0f * g * e.y);
+        const float en = dot2(e_bar, n);
+        r_bar = e_bar;
+        const float2 i_bar = make_float2(-e_bar.x + 2.0f * en * n.x, -e_bar.y + 2.0f * en * n.y);
+        n_bar.x += c2 * e_bar.x + 2.0f * en * i.x;
+        n_bar.y += c2 * e_bar.y + 2.0f * en * i.y;
+        const float2 iv_bar = normalize_adj_hat(i, li, i_bar);
+        b_bar.x += iv_bar.x; b_bar.y += iv_bar.y;
+        a_bar.x -= iv_bar.x; a_bar.y -= iv_bar.y;
+    } else {  // RIS
+        const float mx = -r.x, my = -r.y;
+        const float sin_a = mx * n.y - my * n.x;
+        const float cos_a = mx * n.x + my * n.y;
+        const float ds = 2.0f * g * (sin_a - sc.x);
+        const float dc = 2.0f * g * (cos_a - sc.y);
+        phi_bar += -ds * sc.y + dc * sc.x;
+        const float mbx = ds * n.y + dc * n.x;
+        const float mby = -ds * n.x + dc * n.y;
+        r_bar = make_float2(-mbx, -mby);
+        n_bar.x += -ds * my + dc * mx;
+        n_bar.y += ds * mx + dc * my;
+    }
+    const float2 rv_bar = normalize_adj_hat(r, lr, r_bar);
+    c_bar.x += rv_bar.x; c_bar.y += rv_bar.y;
+    b_bar.x -= rv_bar.x; b_bar.y -= rv_bar.y;
+}
+
 // normalize_adj with the length normalize2 already produced (same values: len = sqrtf(v.v), 1 when v == 0)
 __device__ __forceinline__ float2 normalize_adj_len(const float2 v, const float len, const bool zero, const float2 vh_bar) {
     if (zero) return vh_bar;  // v / 1

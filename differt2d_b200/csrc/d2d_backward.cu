@@ -25,6 +25,33 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// Sums N (a power of two <= 32) per-lane values over the warp in one butterfly: at every stage a lane keeps one half of
+// its values, hands the other half to its partner and adds what it receives, so N values cost N - 1 + (5 - log2 N)
+// shuffles instead of 5 N (8 values: 9 instead of 40).  Returns, in EVERY lane l, the warp total of value number
+// l >> (5 - log2 N).  Must be called by the whole warp.
+template <int N>
+__device__ __forceinline__ float warp_sum_many(float (&v)[N]) {
+    static_assert(N >= 1 && N <= 32 && (N & (N - 1)) == 0, "N must be a power of two");
+    const int lane = threadIdx.x & 31;
+    int stride = 16;
+#pragma unroll
+    for (int n = N; n > 1; n >>= 1) {
+        const bool upper = (lane & stride) != 0;
+#pragma unroll
+        for (int k = 0; k < n / 2; ++k) {
+            const float send = upper ? v[k] : v[k + n / 2];
+            const float keep = upper ? v[k + n / 2] : v[k];
+            v[k] = keep + __shfl_xor_sync(0xffffffffu, send, stride);
+        }
+        stride >>= 1;
+    }
+    float r = v[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        if (o <= stride) r += __shfl_xor_sync(0xffffffffu, r, o);
+    return r;
+}
+
 // Reverse sweep of one path (ImagePath: closed form; FermatPath / MinPath: through the Adam scan, see
 // d2d_solver_adj.cuh).  Returns valid * fun; when the path carries gradient, `has` is set and tx_bar / rx_bar /
 // alpha_bar / oa[] / occ_* are filled (not accumulated).
@@ -98,7 +125,7 @@ __device__ __noinline__ float path_vjp(const SceneTab& T, const KParams& p, cons
     }
     bool alive = true;
     int seg = -1, jj = -1;
-    const float interx = intersects_x<MODE, K, true>(T, p.N, cd, X, alpha, alive, seg, jj);
+    const float interx = intersects_x<MODE, K, true>(T, p.N, cd, X, alpha, x_zero<MODE>(alpha), alive, seg, jj);
     if (!alive) return 0.0f;
     float valid = 1.0f, a_in = 0.0f;
     if (MODE != D2D_MODE_HARD) {
@@ -379,36 +406,46 @@ __device__ __forceinline__ void run_order_bwd(const SceneTab& T, const KParams& 
                 while (pend) {
                     const int j0 = __shfl_sync(0xffffffffu, occ_j, __ffs(pend) - 1);
                     const bool mine = has && occ_j == j0;
-                    float4 v = mine ? occ_bar : make_float4(0.f, 0.f, 0.f, 0.f);
-                    v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-                    if ((threadIdx.x & 31) == 0) {
-                        atomicAdd(&s_obj[4 * j0 + 0], v.x);
-                        atomicAdd(&s_obj[4 * j0 + 1], v.y);
-                        atomicAdd(&s_obj[4 * j0 + 2], v.z);
-                        atomicAdd(&s_obj[4 * j0 + 3], v.w);
-                    }
+                    float v[4] = {mine ? occ_bar.x : 0.f, mine ? occ_bar.y : 0.f, mine ? occ_bar.z : 0.f,
+                                  mine ? occ_bar.w : 0.f};
+                    const float tot = warp_sum_many<4>(v);  // lane l: component l >> 3
+                    if ((threadIdx.x & 7) == 0) atomicAdd(&s_obj[4 * j0 + ((threadIdx.x & 31) >> 3)], tot);
                     pend &= ~__ballot_sync(0xffffffffu, mine);
                 }
             }
             if (K > 0 && s_obj && __any_sync(0xffffffffu, has)) {
-                // every lane holds the same candidate: reduce the interacting objects' cotangents in the warp
+                // every lane holds the same candidate: the 4 K vertex cotangents of its interacting objects go through
+                // ONE butterfly (warp_sum_many) and one shared-memory atomic instruction (this epilogue was 350 of the
+                // 1600 instructions of a visit on the un-prunable leg: 5 shuffles per value, 8 values at order 2)
+                constexpr int NV = K <= 1 ? 4 : (K == 2 ? 8 : 16);
+                float v[NV];
+#pragma unroll
+                for (int q = 0; q < NV; ++q) v[q] = 0.f;
+                bool any_ris = false;
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
-                    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                    float ph = 0.f;
                     if (has) {
-                        v = oa[i].to_vertices(T.w0[cd.c[i]], T.w1[cd.c[i]]);
-                        ph = oa[i].phi;
+                        const float4 u = oa[i].to_vertices(T.w0[cd.c[i]], T.w1[cd.c[i]]);
+                        v[4 * i + 0] = u.x; v[4 * i + 1] = u.y; v[4 * i + 2] = u.z; v[4 * i + 3] = u.w;
                     }
-                    v.x = warp_sum(v.x); v.y = warp_sum(v.y); v.z = warp_sum(v.z); v.w = warp_sum(v.w);
-                    const bool ris = T.kind[cd.c[i]] == D2D_KIND_RIS;
-                    if (ris) ph = warp_sum(ph);
-                    if ((threadIdx.x & 31) == 0) {
-                        atomicAdd(&s_obj[4 * cd.c[i] + 0], v.x);
-                        atomicAdd(&s_obj[4 * cd.c[i] + 1], v.y);
-                        atomicAdd(&s_obj[4 * cd.c[i] + 2], v.z);
-                        atomicAdd(&s_obj[4 * cd.c[i] + 3], v.w);
-                        if (ris) atomicAdd(&s_phi[cd.c[i]], ph);
+                    any_ris = any_ris || T.kind[cd.c[i]] == D2D_KIND_RIS;
+                }
+                const float tot = warp_sum_many<NV>(v);
+                constexpr int kShift = NV == 4 ? 3 : (NV == 8 ? 2 : 1);  // lane l holds value l >> kShift
+                const int lane = threadIdx.x & 31, q = lane >> kShift;
+                if ((lane & ((1 << kShift) - 1)) == 0 && q < 4 * K) {
+                    int obj = cd.c[0];
+#pragma unroll
+                    for (int i = 1; i < K; ++i)
+                        if ((q >> 2) == i) obj = cd.c[i];
+                    atomicAdd(&s_obj[4 * obj + (q & 3)], tot);
+                }
+                if (any_ris) {  // (uniform over the warp)
+#pragma unroll
+                    for (int i = 0; i < K; ++i) {
+                        if (T.kind[cd.c[i]] != D2D_KIND_RIS) continue;
+                        const float ph = warp_sum(has ? oa[i].phi : 0.f);
+                        if (lane == 0) atomicAdd(&s_phi[cd.c[i]], ph);
                     }
                 }
             }
@@ -449,6 +486,7 @@ __global__ void __launch_bounds__(kBlock, D2D_BWD_MIN_CTAS) power_bwd_kernel(con
         }
         return;
     }
+    if (D2D_FOLD_SKIP) T.fold_skip = fold_skip_bound<MODE>(alpha);
     if constexpr (METHOD == D2D_METHOD_IMAGE) {
         if (p.macro) macro_prologue<MODE, TXGRID>(T, p, tile, sh, alpha);
     }

@@ -88,6 +88,7 @@ struct SceneTab {
     int* kind;     // D2D_KIND_*
     short* allowed;  // ascending list of visitable objects
     int n_allowed;
+    float fold_skip;  // fold_skip_bound<MODE>(alpha), set by the kernels that want the shortcut (-inf: never)
 };
 
 __host__ __device__ inline size_t scene_tab_bytes(int N) {
@@ -103,6 +104,7 @@ __device__ __forceinline__ SceneTab carve_tab(unsigned char* smem, int N) {
     T.kind = reinterpret_cast<int*>(T.sc + N);
     T.allowed = reinterpret_cast<short*>(T.kind + N);
     T.n_allowed = 0;
+    T.fold_skip = -CUDART_INF_F;
     return T;
 }
 
@@ -207,6 +209,44 @@ __device__ __forceinline__ float x_zero(float alpha) {
     if (MODE == D2D_MODE_HARD_SIGMOID) return -3.0f / alpha - fabsf(4.0f / alpha) * 1e-5f;
     // sigmoid: 1/(1+expf(-z)) is exactly 0 once expf(-z) overflows (-z > 88.73): z <= -89 is safely there
     return -89.5f / alpha;
+}
+
+// ---- when the occlusion fold cannot matter (smooth logic) -----------------------------------------
+// is_valid = min(a_on, 1 - a_in, a_l) (geometry.py:947-963) with a_in = act(interx), and every test of the fold is
+// hx = min(ta + tol, (1 + tol) - ta, tb + tol, (1 + tol) - tb) <= (1 + 2 tol) / 2 = 0.505 (+ an ulp) whatever ta is:
+// a_in <= act(0.51), hence 1 - a_in >= 1 - act(0.51).  A path whose v0 = min(a_on, a_l) is not above that has
+// validity v0 EXACTLY, whatever the fold returns — for a soft activation (sigmoid, small alpha) that is most of the
+// list: act(0.51) = 0.62 at alpha = 1, and a path that misses its wall or breaks the reflection law has v0 < 0.38.
+// The 4e-6 keeps the shortcut away from the last-bit behaviour of expf (2 ulp) and of the two roundings after it: a
+// skipped fold would have returned 1 - a_in > v0 strictly, so the min, its arg-min and its tie count are unchanged.
+template <int MODE>
+__device__ __forceinline__ float fold_skip_bound(const float alpha) {
+    if (MODE == D2D_MODE_HARD) return -CUDART_INF_F;
+    return (1.0f - act<MODE>(0.51f, alpha)) - 4e-6f;
+}
+
+// Where the fold has to start caring: the largest x' >= xz with 1 - act(x') >= v0 + 2e-6, VERIFIED with the
+// canonical activation (the closed form / fast logarithm below only proposes it).  Tests with hx <= x' cannot bring
+// 1 - a_in down to v0: they are filtered like the ones below x_zero, and the exact divisions run for real
+// occluders only.  Falls back to xz.  (Used by the sigmoid kernels only: in the hard_sigmoid kernels a per-thread
+// threshold instead of the uniform x_zero cost the headline forward 3 % in registers for paths that are nearly all at
+// v0 = 1 there, where fold_start == x_zero anyway.)
+template <int MODE>
+__device__ __forceinline__ float fold_start(const float v0, const float alpha, const float xz) {
+    if (MODE == D2D_MODE_HARD) return xz;
+    const float tgt = (1.0f - v0) - 4e-6f;  // wanted: act(x') <= tgt
+    if (!(tgt > 1e-6f) || !(tgt < 1.0f)) return xz;
+    float x;
+    if (MODE == D2D_MODE_SIGMOID) {
+        x = __logf(__fdividef(tgt, 1.0f - tgt));  // logit
+        x = __fdividef(x - 1e-3f * (1.0f + fabsf(x)), alpha);
+    } else {
+        x = __fdividef(6.0f * tgt - 3.0f, alpha);
+        x = x - 1e-5f * (fabsf(x) + __fdividef(3.0f, alpha));
+    }
+    if (!(x > xz)) return xz;
+    const float a = act<MODE>(x, alpha);
+    return (1.0f - a >= v0 + 2e-6f) ? x : xz;
 }
 
 // ---- geometry -------------------------------------------------------------------------------

@@ -40,6 +40,13 @@ namespace d2d {
 namespace cg = cooperative_groups;
 
 constexpr int kBlock = 128;
+// build switches of this round's cull refinements (1: on; the 0 builds exist for A/B timing, results are identical)
+#ifndef D2D_RULE2_ERROR_SCALED
+#define D2D_RULE2_ERROR_SCALED 1
+#endif
+#ifndef D2D_FOLD_SKIP
+#define D2D_FOLD_SKIP 1
+#endif
 // resident CTAs per SM the kernels are compiled for (register caps 64 / 96 per thread): occupancy hides the
 // instruction-fetch and fixed-latency stalls that dominate these branchy FP32 kernels (profiles/)
 #ifndef D2D_FWD_MIN_CTAS
@@ -48,13 +55,11 @@ constexpr int kBlock = 128;
 #ifndef D2D_BWD_MIN_CTAS
 #if defined(D2D_TU_SOLVER) && D2D_TU_SOLVER
 #define D2D_BWD_MIN_CTAS 5  // FermatPath / MinPath: the reverse sweep through the scan keeps far more state alive
-#elif defined(D2D_TU_MODE) && D2D_TU_MODE == D2D_MODE_SIGMOID
-// sigmoid never saturates: (nearly) every path runs the reverse sweep, whose live state does not fit 64 registers —
-// at 8 CTAs/SM the un-prunable leg spilt 0.5 GB per launch to DRAM (ncu, r02n) for a 1 % gain: 96 registers there
-#define D2D_BWD_MIN_CTAS 5
 #else
 // hard / hard_sigmoid: the sweep runs for the few paths with a non-zero validity, the re-trace wants occupancy:
-// 64 registers; measured 8 > 6 > 5 > 4 > 3 CTAs/SM (r02g, r02j)
+// 64 registers; measured 8 > 6 > 5 > 4 > 3 CTAs/SM (r02g, r02j).  sigmoid (every path runs the sweep): 5 CTAs/SM
+// (96 registers) was on par while the fold ran for every path; since the fold shortcut the kernel is instruction-fetch
+// bound and occupancy wins again: 6.46 ms at 8 CTAs/SM vs 6.78 / 6.79 / 6.96 at 5 / 6 / 4 (r02r)
 #define D2D_BWD_MIN_CTAS 8
 #endif
 #endif
@@ -81,6 +86,7 @@ struct DriverShared {
     int count;               // n_allowed
     int hint[kBlock / 32];   // per warp: the object that blocked its previous path (intersects_x starts its fold there)
     float red[4][4];         // per-warp partials
+    float ext[4][6];         // per-warp partials of the scene extent (make_tile)
     int wcount[2][4];        // survivors per warp segment, double buffered
     int4 list[2][kBlock];    // packed survivors: (c0 | c1 << 16, c2 | c3 << 16, index lo, index hi)
     float4 aux[2][kBlock];   // per survivor: apex (image of the fixed point through all objects) x, y; s-tolerance of
@@ -197,19 +203,43 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     if (!(sx < CUDART_INF_F)) sx = 0.0f;  // empty tile
     if (!(sy < CUDART_INF_F)) sy = 0.0f;
     float ex0 = xmin, ex1 = xmax, ey0 = ymin, ey1 = ymax;  // extent of everything in play (inverted for an empty tile)
-    for (int j = 0; j < p.N; ++j) {    // uniform, N is small next to the candidate count
-        const float4 w = T.w0[j];
-        sx = fmaxf(sx, fmaxf(fabsf(w.x), fabsf(w.x + w.z)));
-        sy = fmaxf(sy, fmaxf(fabsf(w.y), fabsf(w.y + w.w)));
-        ex0 = fminf(ex0, fminf(w.x, w.x + w.z)); ex1 = fmaxf(ex1, fmaxf(w.x, w.x + w.z));
-        ey0 = fminf(ey0, fminf(w.y, w.y + w.w)); ey1 = fmaxf(ey1, fmaxf(w.y, w.y + w.w));
-    }
-    for (int f = 0; f < p.T; ++f) {
-        const float fxx = p.fixed[2 * f], fyy = p.fixed[2 * f + 1];
-        sx = fmaxf(sx, fabsf(fxx));
-        sy = fmaxf(sy, fabsf(fyy));
-        ex0 = fminf(ex0, fxx); ex1 = fmaxf(ex1, fxx);
-        ey0 = fminf(ey0, fyy); ey1 = fmaxf(ey1, fyy);
+    {
+        // objects and fixed points: strided over the CTA, then min / max through shuffles and shared memory (exact and
+        // order-free, so every thread ends up with the same bits as the serial loop over all N objects that each
+        // thread used to run: 3 % of the forward kernel on the city scene)
+        float a0 = 0.f, a1 = 0.f;                                             // max |x|, max |y|
+        float b0 = CUDART_INF_F, b1 = -CUDART_INF_F, c0 = CUDART_INF_F, c1 = -CUDART_INF_F;  // x range, y range
+        for (int j = tid; j < p.N; j += kBlock) {
+            const float4 w = T.w0[j];
+            a0 = fmaxf(a0, fmaxf(fabsf(w.x), fabsf(w.x + w.z)));
+            a1 = fmaxf(a1, fmaxf(fabsf(w.y), fabsf(w.y + w.w)));
+            b0 = fminf(b0, fminf(w.x, w.x + w.z)); b1 = fmaxf(b1, fmaxf(w.x, w.x + w.z));
+            c0 = fminf(c0, fminf(w.y, w.y + w.w)); c1 = fmaxf(c1, fmaxf(w.y, w.y + w.w));
+        }
+        for (int f = tid; f < p.T; f += kBlock) {
+            const float fxx = p.fixed[2 * f], fyy = p.fixed[2 * f + 1];
+            a0 = fmaxf(a0, fabsf(fxx));
+            a1 = fmaxf(a1, fabsf(fyy));
+            b0 = fminf(b0, fxx); b1 = fmaxf(b1, fxx);
+            c0 = fminf(c0, fyy); c1 = fmaxf(c1, fyy);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            a0 = fmaxf(a0, __shfl_xor_sync(0xffffffffu, a0, o)); a1 = fmaxf(a1, __shfl_xor_sync(0xffffffffu, a1, o));
+            b0 = fminf(b0, __shfl_xor_sync(0xffffffffu, b0, o)); b1 = fmaxf(b1, __shfl_xor_sync(0xffffffffu, b1, o));
+            c0 = fminf(c0, __shfl_xor_sync(0xffffffffu, c0, o)); c1 = fmaxf(c1, __shfl_xor_sync(0xffffffffu, c1, o));
+        }
+        if (lane == 0) {
+            sh.ext[warp][0] = a0; sh.ext[warp][1] = a1; sh.ext[warp][2] = b0;
+            sh.ext[warp][3] = b1; sh.ext[warp][4] = c0; sh.ext[warp][5] = c1;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int w = 0; w < kBlock / 32; ++w) {
+            sx = fmaxf(sx, sh.ext[w][0]); sy = fmaxf(sy, sh.ext[w][1]);
+            ex0 = fminf(ex0, sh.ext[w][2]); ex1 = fmaxf(ex1, sh.ext[w][3]);
+            ey0 = fminf(ey0, sh.ext[w][4]); ey1 = fmaxf(ey1, sh.ext[w][5]);
+        }
     }
     t.scale_x = sx;
     t.scale_y = sy;
@@ -351,7 +381,21 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         const float un_eff = unmin - 1.5f * dev - 8.0f * eps * U1;
         const float seg_pb = g_abs_min * un_eff;    // |p - X| >= |g| |u.n|
         const float seg_bA = g1_abs_min * un_eff;   // |X - A| >= |1 + g| |u.n|
+#if D2D_RULE2_ERROR_SCALED
+        // rule (2) needs the DIRECTIONS of the computed segments, not their lengths, and only roughly: a wrong-side
+        // interaction has |e| = 2 in exact arithmetic, and the path is dead as soon as the computed loss reaches
+        // tol - xz (0.01 hard, 0.04 hard_sigmoid at alpha = 100).  Both end points of a computed segment lie within
+        // their error bounds (dev for the point this stage starts from, dX for the one it produces, one lattice
+        // rounding per mirror for the images the construction aims at); a segment 8 times longer than those together
+        // has its direction within 0.126 rad, two of them move e by at most 0.26: |e|^2 >= 3 for the interaction whose
+        // exact residual is 4.  (The fixed requirement 4096 eps S — kept below for the other build — never holds on
+        // lon/lat coordinates, where the whole scene is 60 eps S wide: there the loss test killed 9.6e6 of the 1.76e7
+        // paths that lay on their objects, one by one, in the threads.)
+        const float Lreq = 8.0f * (dXx + dXy + dev + 8.0f * (float)(K + 1) * eps * pow2_floor(S)) + 1e-15f;
+        if (!(seg_pb >= Lreq && seg_bA >= Lreq)) lens_ok = false;
+#else
         if (!(seg_pb >= Lmin && seg_bA >= Lmin)) lens_ok = false;
+#endif
         if (deg_pending) {  // the zero-length object(s) between p and this X: previous point is X, distance |p - X|
             // rule (3) only needs the two COMPUTED points to differ (any non-zero vector normalises to |i_hat|^2 =
             // 1 +- 4 ulp): true distance minus both evaluation errors, not the direction accuracy of rule (2)
@@ -384,7 +428,7 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         if (any_deg) {
             if (deg_dead && 0.98f >= loss_dead) { D2D_COUNT(4); return false; }  // rule (3)
             D2D_COUNT(7);
-        } else if (g_out && lens_ok && 3.9f >= loss_dead) {
+        } else if (g_out && lens_ok && (D2D_RULE2_ERROR_SCALED ? 2.5f : 3.9f) >= loss_dead) {
             D2D_COUNT(5);
             return false;                                           // rule (2)
         }
@@ -817,6 +861,10 @@ __device__ __forceinline__ void for_each_candidate(const SceneTab& T, const KPar
                 }
                 todo = __ballot_sync(0xffffffffu, wk);
             } else if (cull && kApex) {  // warp-level refinement: lane q tests survivor q0 + q against this warp's box
+                // (Running the COMPLETE conservative test again on the warp's own 16 x 2 box — every stage, every rule,
+                // through the out-of-line copy the macro stage uses — was measured: with a handful of survivors per
+                // chunk its lanes are mostly idle, and it cost 0.17 ms per launch on either bench leg for 0.02 ms of
+                // visits saved on the raw city scene, profiles/r02p_ab.txt; removed.)
                 bool wk = false;
                 if (lane < nq && tile.wbox.x <= tile.wbox.z) {  // (a warp without active points skips everything)
                     const int sl = myslot;

@@ -72,6 +72,7 @@ __global__ void __launch_bounds__(kBlock, D2D_FWD_MIN_CTAS) power_fwd_kernel(con
             for (int t = 0; t < (p.reduce_all ? 1 : p.T); ++t) Z[(long long)t * p.R + tile.r] = CUDART_NAN_F;
         return;
     }
+    if (D2D_FOLD_SKIP) T.fold_skip = fold_skip_bound<MODE>(alpha);
     if constexpr (METHOD == D2D_METHOD_IMAGE) {
         if (p.macro) macro_prologue<MODE, TXGRID>(T, p, tile, sh, alpha);
     }

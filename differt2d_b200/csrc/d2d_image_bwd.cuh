@@ -20,6 +20,9 @@ namespace d2d {
 
 __device__ __forceinline__ float fdiv(const float a, const float b) { return __fdividef(a, b); }
 
+template <int MODE>
+__device__ __forceinline__ float act_and_dz(const float x, const float alpha, float& dz);
+
 // act(x) and d act / d z at z = alpha x in one evaluation (the sigmoid's exponential is shared)
 template <int MODE>
 __device__ __forceinline__ float act_and_dz(const float x, const float alpha, float& dz) {
@@ -41,9 +44,21 @@ __device__ __forceinline__ float act_and_dz(const float x, const float alpha, fl
 template <int K>
 struct ImageTrace {
     float2 X[K + 2];
+    float2 U[K + 1];   // unit directions of the segments, as path_loss normalised them
+    float Ls[K + 1];   // ... and their lengths (1 for a zero-length segment)
     float on_s, a_on, a_l, a_in, lx, interx, valid, val, r;
     int on_i, seg, jj;
 };
+
+// d act / d z at z = alpha x from the activation the trace already evaluated there (sigmoid: s (1 - s), no second
+// exponential; same bits as act_and_dz, which forms s the same way)
+template <int MODE>
+__device__ __forceinline__ float dz_from_act(const float a, const float x, const float alpha) {
+    if (MODE == D2D_MODE_SIGMOID) return a * (1.0f - a);
+    float dz;
+    act_and_dz<MODE>(x, alpha, dz);
+    return dz;
+}
 
 // The forward kernel's path evaluation (image_path_on + validity_from_onx, same operations in the same order) that
 // also records the arg-min interaction of on_objects and the arg-max (segment, object) test of the occlusion fold.
@@ -99,7 +114,7 @@ __device__ __forceinline__ bool trace_image_tracked(const SceneTab& T, const KPa
         tr.a_on = act<MODE>(onx, alpha);
         if (tr.a_on == 0.0f) return false;
     }
-    const float loss = path_loss<K>(T, cd, tr.X);
+    const float loss = path_loss_dirs<K>(T, cd, tr.X, tr.U, tr.Ls);
     tr.lx = p.tol - loss;
     tr.a_l = 1.0f;
     if (MODE == D2D_MODE_HARD) {
@@ -112,11 +127,21 @@ __device__ __forceinline__ bool trace_image_tracked(const SceneTab& T, const KPa
     bool alive = true;
     tr.seg = -1;
     tr.jj = -1;
-    tr.interx = intersects_x<MODE, K, true>(T, p.N, cd, tr.X, alpha, alive, tr.seg, tr.jj, hint);
-    if (!alive) return false;
+    tr.interx = -CUDART_INF_F;
     tr.valid = 1.0f;
     tr.a_in = 0.0f;
+    float xz = x_zero<MODE>(alpha);
+    bool fold = true;
     if (MODE != D2D_MODE_HARD) {
+        // the fold cannot matter (fold_skip_bound): validity = min(a_on, a_l) exactly, 1 - a_in is strictly above it
+        // (no tie, the cotangent follows a_on / a_l); otherwise it only has to look for tests above fold_start
+        const float v0 = fminf(tr.a_on, tr.a_l);
+        if (v0 <= T.fold_skip) { fold = false; tr.valid = v0; }
+        else if (MODE == D2D_MODE_SIGMOID && T.fold_skip > -CUDART_INF_F) xz = fold_start<MODE>(v0, alpha, xz);
+    }
+    if (fold) tr.interx = intersects_x<MODE, K, true>(T, p.N, cd, tr.X, alpha, xz, alive, tr.seg, tr.jj, hint);
+    if (!alive) return false;
+    if (MODE != D2D_MODE_HARD && fold) {
         tr.a_in = (tr.interx == -CUDART_INF_F) ? 0.0f : act<MODE>(tr.interx, alpha);
         tr.valid = fminf(fminf(tr.a_on, 1.0f - tr.a_in), tr.a_l);
         if (tr.valid == 0.0f) return false;
@@ -148,9 +173,21 @@ __device__ __forceinline__ void image_reverse_general(const SceneTab& T, const K
             // contains_parametric = minimum(act(s - 0), act(1 - s)) (geometry.py:608-621); jnp.minimum's tie rule
             // (1/2, 1/2) applies to the ACTIVATED values, which tie far more often than the pre-activations do
             const float xg = tr.on_s, xl = 1.0f - tr.on_s;
-            float dg, dl;
-            const float Ag = act_and_dz<MODE>(xg, alpha, dg), Al = act_and_dz<MODE>(xl, alpha, dl);
-            const float wg = Ag < Al ? 1.0f : (Ag == Al ? 0.5f : 0.0f), wl = 1.0f - wg;
+            float dg, dl, wg;
+            // a_on IS the activation of the smaller of the two (onx = min(xg, xl), monotone map); the other one only
+            // matters if it ties with it after rounding, which a sigmoid away from saturation cannot do once the
+            // pre-activations differ by 1e-3 / alpha (slope >= 1e-3 there: 1e-6 apart, 8 ulp): no exponential at all
+            // for nearly every path of a soft-activation run
+            const float xgap = fabsf(xg - xl);
+            if (MODE == D2D_MODE_SIGMOID && tr.a_on < 0.999f && tr.a_on > 1e-30f && alpha * xgap > 1e-3f) {
+                const float dm = tr.a_on * (1.0f - tr.a_on);
+                wg = xg < xl ? 1.0f : 0.0f;
+                dg = dm; dl = dm;  // (the one with weight 0 is not used)
+            } else {
+                const float Ag = act_and_dz<MODE>(xg, alpha, dg), Al = act_and_dz<MODE>(xl, alpha, dl);
+                wg = Ag < Al ? 1.0f : (Ag == Al ? 0.5f : 0.0f);
+            }
+            const float wl = 1.0f - wg;
             const float s_bar = share * alpha * (wg * dg - wl * dl);
             alpha_bar = fmaf(share, wg * xg * dg + wl * xl * dl, alpha_bar);
             if (s_bar != 0.f) {
@@ -169,16 +206,15 @@ __device__ __forceinline__ void image_reverse_general(const SceneTab& T, const K
             }
         }
         if (v3 == tr.valid) {
-            float dz;
-            act_and_dz<MODE>(tr.lx, alpha, dz);
+            const float dz = dz_from_act<MODE>(tr.a_l, tr.lx, alpha);
             const float loss_bar = -share * alpha * dz;
             alpha_bar = fmaf(share, tr.lx * dz, alpha_bar);
             if (loss_bar != 0.f) {
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
                     const int j = cd.c[i];
-                    residual_adj(T.kind[j], X[i], X[i + 1], X[i + 2], T.w1[j], T.sc[j], loss_bar, Xb[i], Xb[i + 1],
-                                 Xb[i + 2], oa[i].n, oa[i].phi);
+                    residual_adj_dirs(T.kind[j], tr.U[i], tr.Ls[i], tr.U[i + 1], tr.Ls[i + 1], T.w1[j], T.sc[j], loss_bar,
+                                      Xb[i], Xb[i + 1], Xb[i + 2], oa[i].n, oa[i].phi);
                 }
             }
         }

@@ -124,6 +124,25 @@ __device__ __forceinline__ float path_loss(const SceneTab& T, const Cand<K>& cd,
     return loss;
 }
 
+// path_loss() that also hands out what it normalised: the K + 1 unit directions and lengths (1 for a zero-length
+// segment, geometry.py:227-230).  Same operations, same order, same bits; the reverse sweep of the loss takes them from
+// here instead of normalising every segment again — twice per interaction, plus the square roots of normalize_adj: 8
+// IEEE square roots and 12 IEEE divisions per order-2 path, a third of the sweep's instruction footprint.
+template <int K>
+__device__ __forceinline__ float path_loss_dirs(const SceneTab& T, const Cand<K>& cd, const float2 (&X)[K + 2],
+                                                float2 (&U)[K + 1], float (&Ls)[K + 1]) {
+    float loss = 0.0f;
+    if (K == 0) return loss;
+    U[0] = normalize2(make_float2(X[1].x - X[0].x, X[1].y - X[0].y), Ls[0]);
+#pragma unroll
+    for (int i = 0; i < K; ++i) {
+        const int j = cd.c[i];
+        U[i + 1] = normalize2(make_float2(X[i + 2].x - X[i + 1].x, X[i + 2].y - X[i + 1].y), Ls[i + 1]);
+        loss = loss + residual_dirs(T.kind[j], U[i], U[i + 1], T.w1[j], T.sc[j]);
+    }
+    return loss;
+}
+
 // Path.intersects_with_objects in pre-activation form (geometry.py:887-904 + :153-173).  Returns interx
 // (-inf: `false_value`).  The double loop runs object-major: one shared-memory read of the object serves the
 // K + 1 segments, whose tests are independent instruction streams (ILP), and the whole fold is ONE loop body
@@ -138,10 +157,10 @@ __device__ __forceinline__ float path_loss(const SceneTab& T, const Cand<K>& cd,
 // list order they scan half the scene first).  max is exact and commutative, so the value does not depend on the order.
 template <int MODE, int K, bool TRACK>
 __device__ __forceinline__ float intersects_x(const SceneTab& T, const int N, const Cand<K>& cd,
-                                              const float2 (&X)[K + 2], const float alpha, bool& alive,
-                                              int& arg_seg, int& arg_j, int* hint = nullptr) {
+                                              const float2 (&X)[K + 2], const float alpha, const float xz,
+                                              bool& alive, int& arg_seg, int& arg_j, int* hint = nullptr) {
+    // `xz`: tests with hx <= xz do not matter (x_zero<MODE>(alpha), or fold_start<MODE>() for this path)
     float interx = -CUDART_INF_F;
-    const float xz = x_zero<MODE>(alpha);
     float cthr = filter_threshold(xz);
     float2 B[K + 1];
     int sa[K + 1], sb[K + 1];
@@ -245,11 +264,17 @@ __device__ __forceinline__ float validity_from_onx(const SceneTab& T, const KPar
         a_l = act<MODE>(lx, alpha);
         if (a_l == 0.0f) { D2D_COUNT(23); return 0.0f; }
     }
-    // 3. occlusion
+    // 3. occlusion — unless it cannot matter (fold_skip_bound): is_valid is then min(a_on, a_l) exactly
+    float xz = x_zero<MODE>(alpha);
+    if (MODE != D2D_MODE_HARD) {
+        const float v0 = fminf(a_on, a_l);
+        if (v0 <= T.fold_skip) return v0;
+        if (MODE == D2D_MODE_SIGMOID && T.fold_skip > -CUDART_INF_F) xz = fold_start<MODE>(v0, alpha, xz);
+    }
     D2D_COUNT(24);
     bool alive = true;
     int seg = 0, jj = 0;
-    const float interx = intersects_x<MODE, K, false>(T, p.N, cd, X, alpha, alive, seg, jj, hint);
+    const float interx = intersects_x<MODE, K, false>(T, p.N, cd, X, alpha, xz, alive, seg, jj, hint);
     if (!alive) return 0.0f;
     if (MODE == D2D_MODE_HARD) return 1.0f;
     const float a_in = (interx == -CUDART_INF_F) ? 0.0f : act<MODE>(interx, alpha);

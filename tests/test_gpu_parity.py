@@ -161,7 +161,10 @@ def _oracle_vjp64(*a, **kw):
 
 @pytest.mark.parametrize("name", ["obstacle", "basic", "geojson_norm"])
 @pytest.mark.parametrize("mode,alpha", [("hard", 100.0), ("hard_sigmoid", 20.0), ("hard_sigmoid", 100.0),
-                                        ("sigmoid", 10.0), ("sigmoid", 100.0)])
+                                        ("sigmoid", 10.0), ("sigmoid", 100.0),
+                                        # soft activations: most paths take the fold shortcut (fold_skip_bound) and the
+                                        # rest start their fold at fold_start — BASELINE config 2's alpha = 1 included
+                                        ("sigmoid", 1.0), ("sigmoid", 3.0), ("hard_sigmoid", 1.0), ("hard_sigmoid", 4.0)])
 @pytest.mark.parametrize("generic", [False, True])
 def test_vjp_against_autograd_oracle(name, mode, alpha, generic):
     """Reverse mode w.r.t. grid points, object vertices, TX and alpha vs torch autograd of the oracle.
