@@ -225,6 +225,19 @@ __device__ __forceinline__ float fold_skip_bound(const float alpha) {
     return (1.0f - act<MODE>(0.51f, alpha)) - 4e-6f;
 }
 
+// The bound at the point of use.  sigmoid: the value the kernel computed once (an exponential); hard_sigmoid: recomputed
+// from alpha (a few uniform operations, and no register held across the whole kernel: as a SceneTab member it cost the
+// 64-register headline forward 1.3 %).  The shortcut is exact, so every kernel that folds may take it.
+template <int MODE>
+__device__ __forceinline__ float fold_skip_of(const SceneTab& T, const float alpha) {
+#if defined(D2D_FOLD_SKIP) && !D2D_FOLD_SKIP
+    return -CUDART_INF_F;
+#else
+    if (MODE == D2D_MODE_HARD_SIGMOID) return fold_skip_bound<MODE>(alpha);
+    return T.fold_skip;
+#endif
+}
+
 // Where the fold has to start caring: the largest x' >= xz with 1 - act(x') >= v0 + 2e-6, VERIFIED with the
 // canonical activation (the closed form / fast logarithm below only proposes it).  Tests with hx <= x' cannot bring
 // 1 - a_in down to v0: they are filtered like the ones below x_zero, and the exact divisions run for real

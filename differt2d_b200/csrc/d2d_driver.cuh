@@ -40,10 +40,7 @@ namespace d2d {
 namespace cg = cooperative_groups;
 
 constexpr int kBlock = 128;
-// build switches of this round's cull refinements (1: on; the 0 builds exist for A/B timing, results are identical)
-#ifndef D2D_RULE2_ERROR_SCALED
-#define D2D_RULE2_ERROR_SCALED 1
-#endif
+// build switch of the fold shortcut (1: on; the 0 build exists for A/B timing, results are identical)
 #ifndef D2D_FOLD_SKIP
 #define D2D_FOLD_SKIP 1
 #endif
@@ -84,7 +81,9 @@ struct Tile {
 
 struct DriverShared {
     int count;               // n_allowed
-    int hint[kBlock / 32];   // per warp: the object that blocked its previous path (intersects_x starts its fold there)
+    int hint[kBlock / 32];   // per warp: the object that blocked its previous path (intersects_x starts its fold there).
+                             // (One slot per LAST OBJECT of the candidate instead — 8 or 32 per warp — was measured: the
+                             // most recent blocker of ANY candidate predicts better, +8 % / +16 % on the forward launch.)
     float red[4][4];         // per-warp partials
     float ext[4][6];         // per-warp partials of the scene extent (make_tile)
     int wcount[2][4];        // survivors per warp segment, double buffered
@@ -177,8 +176,8 @@ __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShar
     const int warp = tid >> 5, lane = tid & 31;
     if (lane == 0) {
         sh.red[warp][0] = xmin; sh.red[warp][1] = ymin; sh.red[warp][2] = xmax; sh.red[warp][3] = ymax;
-        sh.hint[warp] = 0;
     }
+    if (lane == 0) sh.hint[warp] = 0;
     __syncthreads();
     xmin = fminf(fminf(sh.red[0][0], sh.red[1][0]), fminf(sh.red[2][0], sh.red[3][0]));
     ymin = fminf(fminf(sh.red[0][1], sh.red[1][1]), fminf(sh.red[2][1], sh.red[3][1]));
@@ -381,21 +380,11 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         const float un_eff = unmin - 1.5f * dev - 8.0f * eps * U1;
         const float seg_pb = g_abs_min * un_eff;    // |p - X| >= |g| |u.n|
         const float seg_bA = g1_abs_min * un_eff;   // |X - A| >= |1 + g| |u.n|
-#if D2D_RULE2_ERROR_SCALED
-        // rule (2) needs the DIRECTIONS of the computed segments, not their lengths, and only roughly: a wrong-side
-        // interaction has |e| = 2 in exact arithmetic, and the path is dead as soon as the computed loss reaches
-        // tol - xz (0.01 hard, 0.04 hard_sigmoid at alpha = 100).  Both end points of a computed segment lie within
-        // their error bounds (dev for the point this stage starts from, dX for the one it produces, one lattice
-        // rounding per mirror for the images the construction aims at); a segment 8 times longer than those together
-        // has its direction within 0.126 rad, two of them move e by at most 0.26: |e|^2 >= 3 for the interaction whose
-        // exact residual is 4.  (The fixed requirement 4096 eps S — kept below for the other build — never holds on
-        // lon/lat coordinates, where the whole scene is 60 eps S wide: there the loss test killed 9.6e6 of the 1.76e7
-        // paths that lay on their objects, one by one, in the threads.)
-        const float Lreq = 8.0f * (dXx + dXy + dev + 8.0f * (float)(K + 1) * eps * pow2_floor(S)) + 1e-15f;
-        if (!(seg_pb >= Lreq && seg_bA >= Lreq)) lens_ok = false;
-#else
+        // (An error-scaled requirement — 8 x the end points' own error bounds instead of the fixed 4096 eps S, which
+        // never holds on lon/lat coordinates — was measured: rule (2) then fires on the raw city scene, and the forward
+        // launch got 1 % SLOWER on both coordinate variants, profiles/r02p_ab.txt; the candidates it removes are cheap
+        // ones.  Removed.)
         if (!(seg_pb >= Lmin && seg_bA >= Lmin)) lens_ok = false;
-#endif
         if (deg_pending) {  // the zero-length object(s) between p and this X: previous point is X, distance |p - X|
             // rule (3) only needs the two COMPUTED points to differ (any non-zero vector normalises to |i_hat|^2 =
             // 1 +- 4 ulp): true distance minus both evaluation errors, not the direction accuracy of rule (2)
@@ -428,7 +417,7 @@ __device__ __forceinline__ bool tile_may_be_valid(const SceneTab& T, const int (
         if (any_deg) {
             if (deg_dead && 0.98f >= loss_dead) { D2D_COUNT(4); return false; }  // rule (3)
             D2D_COUNT(7);
-        } else if (g_out && lens_ok && (D2D_RULE2_ERROR_SCALED ? 2.5f : 3.9f) >= loss_dead) {
+        } else if (g_out && lens_ok && 3.9f >= loss_dead) {
             D2D_COUNT(5);
             return false;                                           // rule (2)
         }

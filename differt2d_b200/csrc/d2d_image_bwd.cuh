@@ -136,7 +136,7 @@ __device__ __forceinline__ bool trace_image_tracked(const SceneTab& T, const KPa
         // the fold cannot matter (fold_skip_bound): validity = min(a_on, a_l) exactly, 1 - a_in is strictly above it
         // (no tie, the cotangent follows a_on / a_l); otherwise it only has to look for tests above fold_start
         const float v0 = fminf(tr.a_on, tr.a_l);
-        if (v0 <= T.fold_skip) { fold = false; tr.valid = v0; }
+        if (v0 <= fold_skip_of<MODE>(T, alpha)) { fold = false; tr.valid = v0; }
         else if (MODE == D2D_MODE_SIGMOID && T.fold_skip > -CUDART_INF_F) xz = fold_start<MODE>(v0, alpha, xz);
     }
     if (fold) tr.interx = intersects_x<MODE, K, true>(T, p.N, cd, tr.X, alpha, xz, alive, tr.seg, tr.jj, hint);

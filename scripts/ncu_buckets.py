@@ -5,30 +5,71 @@
 Run here (no GPU needed)."""
 import csv, os, re, subprocess, sys, tempfile, collections
 
-BUCKETS = [  # (name, file, first line, last line) — checked innermost first
-    ("fold intersects_x", "d2d_trace.cuh", 139, 199),
-    ("hit_exact", "d2d_device.cuh", 307, 315),
-    ("path_loss", "d2d_trace.cuh", 111, 125),
-    ("image_path_on", "d2d_trace.cuh", 39, 80),
-    ("trace_image_tracked", "d2d_image_bwd.cuh", 51, 126),
-    ("image_reverse", "d2d_image_bwd.cuh", 128, 320),
-    ("path_value", "d2d_trace.cuh", 201, 207),
-    ("validity_from_onx", "d2d_trace.cuh", 209, 258),
-    ("tile_may_be_valid", "d2d_driver.cuh", 253, 394),
-    ("tile_may_be_valid_tx", "d2d_driver.cuh", 411, 528),
-    ("warp_may_be_valid", "d2d_driver.cuh", 537, 559),
-    ("test_candidate", "d2d_driver.cuh", 561, 642),
-    ("macro_prologue", "d2d_driver.cuh", 677, 722),
-    ("mask_prologue/bitmap", "d2d_driver.cuh", 653, 675),
-    ("mask_prologue/bitmap", "d2d_driver.cuh", 724, 738),
-    ("chunk driver", "d2d_driver.cuh", 740, 898),
-    ("make_tile", "d2d_driver.cuh", 133, 220),
-    ("build_tab", "d2d_device.cuh", 109, 144),
-    ("visit (forward.cu)", "d2d_forward.cu", 17, 56),
-    ("visit (backward.cu)", "d2d_backward.cu", 316, 416),
-    ("kernel body", "d2d_forward.cu", 57, 200),
-    ("kernel body", "d2d_backward.cu", 417, 620),
+# bucket -> (file, function names whose bodies belong to it); line ranges are read from the CURRENT sources
+FUNCS = [
+    ("fold intersects_x", "d2d_trace.cuh", ["intersects_x"]),
+    ("hit_exact", "d2d_device.cuh", ["hit_exact"]),
+    ("path_loss", "d2d_trace.cuh", ["path_loss", "path_loss_dirs"]),
+    ("normalize2 / residual", "d2d_device.cuh", ["normalize2", "residual_dirs", "residual"]),
+    ("back_project / to_parametric / mirror", "d2d_device.cuh", ["back_project", "to_parametric", "mirror"]),
+    ("act", "d2d_device.cuh", ["act", "act_is_zero", "act_is_one", "act_dz", "fold_skip_bound", "fold_start", "fold_skip_of"]),
+    ("image_path_on", "d2d_trace.cuh", ["image_path_on", "image_path", "image_apex"]),
+    ("trace_image_tracked", "d2d_image_bwd.cuh", ["trace_image_tracked"]),
+    ("image_reverse", "d2d_image_bwd.cuh", ["image_reverse_general", "image_reverse", "act_and_dz", "dz_from_act", "fdiv"]),
+    ("adjoint pieces", "d2d_adjoint.cuh", ["normalize_adj", "residual_adj", "normalize_adj_hat", "residual_adj_dirs", "dot2", "to_vertices"]),
+    ("path_value / path_length", "d2d_trace.cuh", ["path_value"]),
+    ("path_value / path_length", "d2d_device.cuh", ["path_length"]),
+    ("validity_from_onx", "d2d_trace.cuh", ["validity_from_onx", "validity", "on_objects_x"]),
+    ("tile_may_be_valid", "d2d_driver.cuh", ["tile_may_be_valid", "pow2_floor"]),
+    ("tile_may_be_valid_tx", "d2d_driver.cuh", ["tile_may_be_valid_tx"]),
+    ("warp_may_be_valid", "d2d_driver.cuh", ["warp_may_be_valid"]),
+    ("test_candidate", "d2d_driver.cuh", ["test_candidate_inline", "test_candidate"]),
+    ("macro_prologue", "d2d_driver.cuh", ["macro_prologue"]),
+    ("mask_prologue/bitmap", "d2d_driver.cuh", ["bitmap_prefix", "mask_prologue", "mask_bitmap_fits"]),
+    ("chunk driver", "d2d_driver.cuh", ["for_each_candidate", "order_count", "hint_slot"]),
+    ("make_tile", "d2d_driver.cuh", ["make_tile"]),
+    ("build_tab", "d2d_device.cuh", ["build_tab", "carve_tab"]),
+    ("visit (forward.cu)", "d2d_forward.cu", ["run_order"]),
+    ("visit + reductions (backward.cu)", "d2d_backward.cu", ["run_order_bwd", "warp_sum", "warp_sum_many", "path_vjp"]),
+    ("kernel body", "d2d_forward.cu", ["power_fwd_kernel"]),
+    ("kernel body", "d2d_backward.cu", ["power_bwd_kernel"]),
 ]
+
+
+def _ranges():
+    """(name, file, first, last) for every listed function: from its signature line to the line before the next
+    top-level definition (a line starting with `template`, `__device__`, `__global__`, `struct`, `static`, `inline`, `//`
+    at column 0 after a closing brace at column 0)."""
+    here = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "differt2d_b200", "csrc")
+    out = []
+    cache = {}
+    for name, f, fns in FUNCS:
+        if f not in cache:
+            cache[f] = open(os.path.join(here, f)).read().splitlines()
+        lines = cache[f]
+        for fn in fns:
+            pat = re.compile(r"\b" + re.escape(fn) + r"\s*\(")
+            for i, l in enumerate(lines):
+                if not pat.search(l):
+                    continue
+                # a definition: the signature is at nesting depth 0 and a '{' follows before a ';'
+                if not re.match(r"^(template|__device__|__global__|static|inline|__host__|\s{0,4}__device__)", l) and not (i > 0 and re.match(r"^(template|__device__|__global__|static)", lines[i - 1])):
+                    continue
+                j = i
+                while j < len(lines) and "{" not in lines[j] and ";" not in lines[j]:
+                    j += 1
+                if j >= len(lines) or ";" in lines[j].split("{")[0]:
+                    continue  # a declaration
+                # body ends at the first line that is exactly "}" (column 0) or "    }" for members
+                indent = len(l) - len(l.lstrip())
+                k = j
+                while k < len(lines) and lines[k].rstrip() != " " * indent + "}":
+                    k += 1
+                out.append((name, f, i + 1, min(k + 1, len(lines))))
+    return out
+
+
+BUCKETS = _ranges()
 
 rep, obj, ksub = sys.argv[1:4]
 tmp = tempfile.mkdtemp()
