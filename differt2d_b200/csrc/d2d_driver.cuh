@@ -52,11 +52,14 @@ constexpr int kBlock = 128;
 #ifndef D2D_BWD_MIN_CTAS
 #if defined(D2D_TU_SOLVER) && D2D_TU_SOLVER
 #define D2D_BWD_MIN_CTAS 5  // FermatPath / MinPath: the reverse sweep through the scan keeps far more state alive
+#elif defined(D2D_TU_MODE) && D2D_TU_MODE == D2D_MODE_SIGMOID
+// sigmoid never saturates: every path runs the reverse sweep, whose live state does not fit 64 registers.  At 8
+// CTAs/SM the dense leg is 2 % faster (4.98 vs 5.10 ms; 7: 5.02, 6: 5.23, r02t) but its spills no longer fit the L2:
+// 1.08 GB of DRAM writes per launch (r02y) against 19 MB at 96 registers.  Not worth 2 %.
+#define D2D_BWD_MIN_CTAS 5
 #else
 // hard / hard_sigmoid: the sweep runs for the few paths with a non-zero validity, the re-trace wants occupancy:
-// 64 registers; measured 8 > 6 > 5 > 4 > 3 CTAs/SM (r02g, r02j).  sigmoid (every path runs the sweep): 5 CTAs/SM
-// (96 registers) was on par while the fold ran for every path; since the fold shortcut the kernel is instruction-fetch
-// bound and occupancy wins again: 6.46 ms at 8 CTAs/SM vs 6.78 / 6.79 / 6.96 at 5 / 6 / 4 (r02r)
+// 64 registers; measured 8 > 6 > 5 > 4 > 3 CTAs/SM (r02g, r02j)
 #define D2D_BWD_MIN_CTAS 8
 #endif
 #endif

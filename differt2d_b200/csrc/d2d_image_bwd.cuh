@@ -114,7 +114,10 @@ __device__ __forceinline__ bool trace_image_tracked(const SceneTab& T, const KPa
         tr.a_on = act<MODE>(onx, alpha);
         if (tr.a_on == 0.0f) return false;
     }
-    const float loss = path_loss_dirs<K>(T, cd, tr.X, tr.U, tr.Ls);
+    // sigmoid: (nearly) every path goes on to the reverse sweep, which takes the normalised segments from here.  The
+    // other logics reverse a path in a hundred: keeping 3 (K + 1) more values alive through the fold cost their
+    // un-masked re-trace (the fused value + VJP launch) 7 % at 64 registers; the sweep normalises again there.
+    const float loss = (MODE == D2D_MODE_SIGMOID) ? path_loss_dirs<K>(T, cd, tr.X, tr.U, tr.Ls) : path_loss<K>(T, cd, tr.X);
     tr.lx = p.tol - loss;
     tr.a_l = 1.0f;
     if (MODE == D2D_MODE_HARD) {
@@ -210,10 +213,18 @@ __device__ __forceinline__ void image_reverse_general(const SceneTab& T, const K
             const float loss_bar = -share * alpha * dz;
             alpha_bar = fmaf(share, tr.lx * dz, alpha_bar);
             if (loss_bar != 0.f) {
+                float2 U[K + 1];
+                float Ls[K + 1];
+                if (MODE == D2D_MODE_SIGMOID) {
+#pragma unroll
+                    for (int i = 0; i <= K; ++i) { U[i] = tr.U[i]; Ls[i] = tr.Ls[i]; }
+                } else {
+                    path_loss_dirs<K>(T, cd, X, U, Ls);  // the trace's own bits again (see trace_image_tracked)
+                }
 #pragma unroll
                 for (int i = 0; i < K; ++i) {
                     const int j = cd.c[i];
-                    residual_adj_dirs(T.kind[j], tr.U[i], tr.Ls[i], tr.U[i + 1], tr.Ls[i + 1], T.w1[j], T.sc[j], loss_bar,
+                    residual_adj_dirs(T.kind[j], U[i], Ls[i], U[i + 1], Ls[i + 1], T.w1[j], T.sc[j], loss_bar,
                                       Xb[i], Xb[i + 1], Xb[i + 2], oa[i].n, oa[i].phi);
                 }
             }

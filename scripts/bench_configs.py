@@ -54,7 +54,7 @@ def main():
         print(json.dumps(line), flush=True)
         out.append(line)
 
-    want = lambda k: not a.only or a.only == k  # noqa: E731
+    want = lambda k: not a.only or k in a.only.split(",")  # noqa: E731
 
     if want("cfg1"):
         sc = d.Scene.square_scene_with_obstacle()
