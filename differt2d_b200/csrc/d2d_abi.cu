@@ -143,6 +143,8 @@ int pack(const D2DProblem* p, d2d::KParams& k) {
     k.alpha_dev = p->alpha_dev;
     k.R = p->n_grid;
     k.grid_cols = (p->grid_cols > 0 && p->n_grid % p->grid_cols == 0) ? p->grid_cols : 0;
+    if (k.grid_cols > 0 && p->n_grid / k.grid_cols > 0x3fffffffLL) k.grid_cols = 0;  // (rows as an int in the kernels)
+    k.grid_rows = k.grid_cols > 0 ? (int)(p->n_grid / k.grid_cols) : 0;
     k.cull = p->no_cull ? 0 : 4;  // non-zero: safety factor applied to the cull's first-order error bound
     k.N = p->n_objects;
     k.T = p->n_fixed;

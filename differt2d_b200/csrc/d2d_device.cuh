@@ -54,6 +54,8 @@ struct KParams {
     const float* alpha_dev;
     long long R;
     int grid_cols;         // row length of the grid when it is a row-major n x m mesh (0: unknown)
+    int grid_rows;         // R / grid_cols, set by the launcher with grid_cols (the kernels map CTAs to tiles in 32-bit
+                           // arithmetic: four 64-bit divisions per thread were 2 % of the forward launch)
     int cull;              // tile-level candidate culling on/off (results are identical either way)
     int slices;            // gridDim.y: CTAs sharing one tile, each walking every slices-th chunk of candidates
     int shard_index, shard_count;  // multi-GPU candidate sharding: this launch owns virtual slices shard_index * slices + y

@@ -142,20 +142,20 @@ inline cudaError_t launch_tiles(void (*kern)(KArgs...), const KParams& p, const 
 __device__ inline Tile make_tile(const KParams& p, const SceneTab& T, DriverShared& sh) {
     Tile t;
     const int tid = threadIdx.x;
-    if (p.grid_cols > 0 && p.R % p.grid_cols == 0) {
-        const long long rows = p.R / p.grid_cols;
-        const int tiles_x = (p.grid_cols + kTileCols - 1) / kTileCols;
-        long long by = blockIdx.x / tiles_x;
-        int bx = (int)(blockIdx.x % tiles_x);
+    if (p.grid_cols > 0) {  // (the launcher sets grid_cols / grid_rows for a whole n x m mesh only)
+        const int rows = p.grid_rows;
+        const unsigned tiles_x = (unsigned)(p.grid_cols + kTileCols - 1) / kTileCols;
+        unsigned by = blockIdx.x / tiles_x;
+        unsigned bx = blockIdx.x - by * tiles_x;
         if (p.cluster) {  // 8 consecutive CTAs (one cluster) = 2 x 4 neighbouring tiles
-            const int macro_x = (tiles_x + kMacroTilesX - 1) / kMacroTilesX;
-            const long long cid = blockIdx.x / kCluster;
-            const int rk = (int)(blockIdx.x % kCluster);
-            bx = kMacroTilesX * (int)(cid % macro_x) + (rk % kMacroTilesX);
-            by = kMacroTilesY * (cid / macro_x) + (rk / kMacroTilesX);
+            const unsigned macro_x = (tiles_x + kMacroTilesX - 1) / kMacroTilesX;
+            const unsigned cid = blockIdx.x / kCluster, rk = blockIdx.x % kCluster;
+            const unsigned cy = cid / macro_x, cx = cid - cy * macro_x;
+            bx = kMacroTilesX * cx + (rk % kMacroTilesX);
+            by = kMacroTilesY * cy + (rk / kMacroTilesX);
         }
-        const int col = bx * kTileCols + (tid & (kTileCols - 1));
-        const long long row = by * kTileRows + (tid / kTileCols);
+        const int col = (int)(bx * kTileCols) + (tid & (kTileCols - 1));
+        const long long row = (long long)by * kTileRows + (tid / kTileCols);
         t.active = col < p.grid_cols && row < rows;
         t.r = row * p.grid_cols + col;
     } else {
