@@ -394,3 +394,45 @@ def test_dual_number_oracle_other_roles_and_objects():
             np.testing.assert_allclose(a[k].reshape(-1), want, rtol=2e-5, atol=2e-6 * scale, err_msg=f"{role} {mode} {k}")
         if mode != "hard" and role == "receivers":
             assert np.abs(a["phis"]).max() > 0
+
+
+@pytest.mark.parametrize("function,alpha", [("sigmoid", 0.5), ("sigmoid", 1.0), ("sigmoid", 3.0), ("sigmoid", 10.0),
+                                            ("hard_sigmoid", 1.0), ("hard_sigmoid", 4.0), ("hard_sigmoid", 100.0)])
+@pytest.mark.parametrize("scene", ["obstacle", "basic"])
+def test_fold_shortcut_claim_holds_in_the_reference_arithmetic(scene, function, alpha):
+    """The kernels skip the occlusion fold of a path whose min(a_on, a_l) is not above 1 - act(0.51) - 4e-6
+    (csrc/d2d_device.cuh:fold_skip_bound) and return that min as the validity.  This pins the claim itself on the
+    restated reference (geometry.py:908-963 literal, fp32): (i) no test of the fold ever activates above act(0.51), and
+    (ii) wherever the bound holds, is_valid — computed WITH the fold — equals min(on_objects, loss < tol) bit for bit."""
+    sc = R.square_scene_with_obstacle() if scene == "obstacle" else R.basic_scene()
+    logic = R.Logic(True, alpha, function)
+    tx = list(sc.transmitters.values())[0]
+    bb = sc.bounding_box()
+    rng = np.random.default_rng(3)
+    n = 20
+    xs = torch.tensor(np.sort(rng.uniform(float(bb[0][0]), float(bb[1][0]), n)).astype(np.float32))
+    ys = torch.tensor(np.sort(rng.uniform(float(bb[0][1]), float(bb[1][1]), n)).astype(np.float32))
+    Y, X = torch.meshgrid(ys, xs, indexing="ij")
+    rx = torch.stack([X, Y], -1)
+    a_max = logic.activation(R._c(0.51))
+    bound = (torch.tensor(1.0) - a_max) - 4e-6
+    skipped = total = 0
+    for cand in R.all_path_candidates(sc.n, 0, 2):
+        xys, loss = R.from_tx_objects_rx(sc, "image", tx, cand, rx)
+        a_on = R.on_objects(sc, cand, xys, logic)
+        a_on = a_on if (torch.is_tensor(a_on) and a_on.ndim) else torch.ones(n, n) * a_on
+        a_l = torch.nan_to_num(logic.lt(loss, R._c(1e-2)) * torch.ones(n, n))
+        a_in = R.intersects_with_objects(sc, cand, xys, logic)
+        a_in = a_in if (torch.is_tensor(a_in) and a_in.ndim) else torch.ones(n, n) * a_in
+        assert bool((a_in <= a_max).all()), "a test of the fold activated above act(0.51)"
+        valid = R.is_valid(sc, cand, xys, loss, logic)
+        valid = valid if valid.ndim else torch.ones(n, n) * valid
+        v0 = torch.minimum(a_on, a_l)
+        m = v0 <= bound
+        skipped += int(m.sum())
+        total += m.numel()
+        assert torch.equal(valid[m], v0[m]), "the validity depends on the fold where the shortcut says it cannot"
+    if function == "sigmoid" and alpha <= 1.0:
+        assert skipped > total // 2  # the regime the shortcut exists for (3/4 of the paths at alpha = 1)
+    if function == "hard_sigmoid" and alpha >= 100.0:
+        assert skipped == 0  # act(0.51) saturates: the bound is negative, the shortcut never fires
